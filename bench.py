@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- CCA hot-path benchmark (BASELINE.json metric).
+
+metric  : CCA fwd+bwd pixels/s @ B x 512 x 97 x 97, R=2  (pixels counted once per step)
+step    : one pass of the hot path over one synthetic batch = the drop-in
+          ``cc_attention.CrissCrossAttention`` module applied R=2 times (networks/ccnet.py:118-119)
+          forward + backward, fp32, B=8 per GPU (weak scaling: images are sharded across ranks,
+          the op needs no collective; DDP all-reduces the 7 parameter grads only).
+value   : x resident in HBM.          e2e : same step, x from pinned host memory, y and dx copied back.
+roofline: the CCA operator itself (all kernels of one op fwd+bwd step, our .so), algorithmic bytes of
+          SURVEY.md 8(d) over the CUDA-event time of those launches.
+--impl reference : the reference module's CPU path (oracle module port; the Python reference cannot
+          travel to the GPU box) on the host cores, bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(B=8, C=512, H=97, W=97, R=2)
+METRIC = "cca_fwd_bwd_pixels_per_s"
+UNIT = "pixels/s"
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def shard_images(global_batch: int, rank: int, world: int):
+    """Image indices of ``rank`` when ``global_batch`` images are dealt to ``world`` ranks (engine.py:86-88)."""
+    per = global_batch // world
+    return list(range(rank * per, (rank + 1) * per))
+
+
+def alg_bytes(B, C, H, W, esize, fwd=True, bwd=True):
+    """fwd = s*N*(2Cq+2C), bwd = s*N*(4Cq+4C) per recurrence step."""
+    N, Cq = B * H * W, C // 8
+    return esize * N * ((2 * Cq + 2 * C) * (1 if fwd else 0) + (4 * Cq + 4 * C) * (1 if bwd else 0))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_run(steps: int, warmup: int, sample_b: int = 2):
+    """The reference module's CPU path (oracle module port, torch CPU ops, all host threads)."""
+    from oracle.cca_oracle import CrissCrossAttentionOracle, rcca_forward
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    C, H, W, R = CFG["C"], CFG["H"], CFG["W"], CFG["R"]
+    m = CrissCrossAttentionOracle(C)
+    with torch.no_grad():
+        m.gamma.fill_(1.0)
+    x = torch.randn(sample_b, C, H, W, requires_grad=True)
+    g = torch.randn(sample_b, C, H, W)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        y = rcca_forward(m, x, R)
+        (y * g).sum().backward()
+        dt = time.perf_counter() - t0
+        x.grad = None
+        m.zero_grad(set_to_none=True)
+        if it >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return {"value": sample_b * H * W * len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": cores,
+            "sample": f"B={sample_b} of the B=8 workload ({sample_b}x{C}x{H}x{W}, R={R}, fwd+bwd, fp32), "
+                      f"{len(times)} timed steps after {warmup} warm-up"}
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    r = cpu_reference_run(max(1, min(args.steps, 5)), max(1, min(args.warmup, 1)))
+    line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(), "note": "reference module CPU path (oracle port), bounded sample"},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_name():
+    return (f"CrissCrossAttention module x R={CFG['R']} fwd+bwd, B={CFG['B']}/GPU C={CFG['C']} Cq={CFG['C'] // 8} "
+            f"{CFG['H']}x{CFG['W']} fp32 (BASELINE configs[1])")
+
+
+def time_events(fn, steps, warmup, barrier=None):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    return e0.elapsed_time(e1) / steps          # ms per step
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (ccnet_b200 has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from ccnet_b200 import RCCA, capi, cca_backward, cca_forward
+    lib = capi.load()
+    assert lib.cca_b200_device_ok() == 1, "not an sm_100 device"
+
+    B, C, H, W, R = CFG["B"], CFG["C"], CFG["H"], CFG["W"], CFG["R"]
+    Cq = C // 8
+    dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[args.dtype]
+    esize = 4 if dtype == torch.float32 else 2
+    torch.manual_seed(1234 + rank)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    model = RCCA(C, recurrence=R, impl=args.kernels).to(dev)
+    with torch.no_grad():
+        model.cca.gamma.fill_(1.0)
+    if dtype == torch.bfloat16:
+        model = model.to(torch.bfloat16)
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank]) if world > 1 else model
+
+    x_host = torch.randn(B, C, H, W, dtype=dtype).pin_memory()
+    g = torch.randn(B, C, H, W, device=dev, dtype=dtype)
+    x = x_host.to(dev).requires_grad_(True)
+    y_host = torch.empty_like(x_host).pin_memory()
+    dx_host = torch.empty_like(x_host).pin_memory()
+
+    def step_resident():
+        y = net(x)
+        (y * g).sum().backward()
+        x.grad = None
+        net.zero_grad(set_to_none=True)
+
+    def step_e2e():
+        xd = x_host.to(dev, non_blocking=True).requires_grad_(True)
+        y = net(xd)
+        (y * g).sum().backward()
+        y_host.copy_(y.detach(), non_blocking=True)
+        dx_host.copy_(xd.grad, non_blocking=True)
+        net.zero_grad(set_to_none=True)
+        torch.cuda.current_stream().synchronize()
+
+    barrier = (lambda: dist.barrier()) if world > 1 else None
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- main timed region (module level, resident) -----------------------------------------
+    n0 = capi.launch_count()
+    with ClockSampler(local_rank) as clk:
+        ms = time_events(step_resident, args.steps, args.warmup, barrier)
+    launches = (capi.launch_count() - n0) * args.steps // (args.steps + args.warmup)
+    ms = max_over_ranks(ms)
+    px = B * H * W * world
+    value = px / (ms * 1e-3)
+
+    # ---- e2e (host buffers) ---------------------------------------------------------------------
+    ms_e2e = max_over_ranks(time_events(step_e2e, max(3, args.steps // 2), 3, barrier))
+    e2e = {"value": px / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+           "h2d_bytes_per_step": x_host.numel() * esize, "d2h_bytes_per_step": 2 * x_host.numel() * esize,
+           "note": "x from pinned host memory; y and dx copied back to pinned host memory every step"}
+
+    # ---- operator-only timings (the kernels of this repo) -> roofline ---------------------------
+    q = torch.randn(B, Cq, H, W, device=dev, dtype=dtype) * 0.58
+    k = torch.randn(B, Cq, H, W, device=dev, dtype=dtype) * 0.58
+    v = torch.randn(B, C, H, W, device=dev, dtype=dtype) * 0.58
+    do = torch.randn(B, C, H, W, device=dev, dtype=dtype)
+    out, lse = cca_forward(q, k, v, impl=args.kernels)
+    bimpl = "auto" if args.kernels == "tc" else args.kernels
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > L2 (126 MB)
+
+    def op_time(fn, iters=10):
+        ts = []
+        for _ in range(3):
+            fn()
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return sum(ts) / len(ts), ts[0]
+
+    n1 = capi.launch_count()
+    f_avg, f_min = op_time(lambda: cca_forward(q, k, v, impl=args.kernels))
+    nf = (capi.launch_count() - n1) // 13
+    n1 = capi.launch_count()
+    b_avg, b_min = op_time(lambda: cca_backward(do, q, k, v, out, lse, impl=bimpl))
+    nb = (capi.launch_count() - n1) // 13
+    peak, peak_src = measured_peaks()
+    bytes_f, bytes_b = alg_bytes(B, C, H, W, esize, True, False), alg_bytes(B, C, H, W, esize, False, True)
+    dom_is_bwd = b_avg >= f_avg
+    dom_bytes, dom_ms = (bytes_b, b_avg) if dom_is_bwd else (bytes_f, f_avg)
+    ach = dom_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "cca backward op (delta + column pass + row pass)" if dom_is_bwd
+                else "cca forward op (column pass + row pass)",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "launches_per_op": nb if dom_is_bwd else nf,
+                "op_fwd": {"ms": f_avg, "ms_min": f_min, "alg_bytes": bytes_f, "gbs": bytes_f / f_avg / 1e6,
+                           "frac": bytes_f / f_avg / 1e6 / peak, "launches": nf},
+                "op_bwd": {"ms": b_avg, "ms_min": b_min, "alg_bytes": bytes_b, "gbs": bytes_b / b_avg / 1e6,
+                           "frac": bytes_b / b_avg / 1e6 / peak, "launches": nb},
+                "op_fwd_bwd_pixels_per_s_R2": B * H * W / (R * (f_avg + b_avg) * 1e-3),
+                "timing": "CUDA events on torch's current stream (the launching stream), L2 flushed between iterations"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_reference_run(3, 1)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32" if dtype == torch.float32 else "bf16", "data": "synthetic",
+                "config": {"workload": workload_name(), "global_batch": B * world, "kernels": args.kernels,
+                           "l2": "working set (x,y,dy,q,k,v,out: >1 GB) exceeds the 126 MB L2; no explicit flush in "
+                                 "the module loop, explicit 256 MB flush between operator-only iterations",
+                           "parallelism": f"dp{world} (image-sharded, DDP grad all-reduce only)"},
+                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--kernels", default="auto", choices=["auto", "simt", "tc"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

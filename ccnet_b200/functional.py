@@ -1,0 +1,96 @@
+"""Tensor-level entry points of the operator: ``cca_forward`` / ``cca_backward`` / ``cca``.
+
+Host-side mirror of the reference's op boundary (cc_attention/functions.py:38-47): the caller
+hands NCHW q, k, v; the extension returns out (and lse for backward).  Everything numerical
+happens in the CUDA library behind the C ABI; PyTorch only owns memory, streams and autograd.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import capi
+
+_DTYPES = {torch.float32: capi.CCA_F32, torch.bfloat16: capi.CCA_BF16}
+_IMPL_FLAGS = {"auto": capi.CCA_FLAG_AUTO, "simt": capi.CCA_FLAG_FORCE_SIMT, "tc": capi.CCA_FLAG_FORCE_TC}
+
+
+def _check_inputs(q, k, v):
+    if not (q.is_cuda and k.is_cuda and v.is_cuda):
+        raise RuntimeError("ccnet_b200: criss-cross attention needs CUDA tensors on a B200 "
+                           "(there is no CPU path in this package)")
+    if q.dtype not in _DTYPES or k.dtype != q.dtype or v.dtype != q.dtype:
+        raise RuntimeError(f"ccnet_b200: q,k,v must share dtype float32 or bfloat16, got "
+                           f"{q.dtype},{k.dtype},{v.dtype}")
+    if q.dim() != 4 or k.shape != q.shape or v.dim() != 4 or v.shape[0] != q.shape[0] or v.shape[2:] != q.shape[2:]:
+        raise RuntimeError(f"ccnet_b200: expected q,k [B,Cq,H,W] and v [B,C,H,W], got "
+                           f"{tuple(q.shape)},{tuple(k.shape)},{tuple(v.shape)}")
+    if not (q.device == k.device == v.device):
+        raise RuntimeError("ccnet_b200: q,k,v must be on the same device")
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def cca_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, impl: str = "auto"):
+    """One criss-cross step: returns (out[B,C,H,W], lse[B,H,W] fp32)."""
+    _check_inputs(q, k, v)
+    lib = capi.load()
+    q, k, v = q.contiguous(), k.contiguous(), v.contiguous()   # reference calls .contiguous() too
+    B, Cq, H, W = q.shape
+    C = v.shape[1]
+    dt = _DTYPES[q.dtype]
+    with torch.cuda.device(q.device):
+        out = torch.empty_like(v)
+        lse = torch.empty((B, H, W), dtype=torch.float32, device=q.device)
+        nws = lib.cca_b200_workspace_bytes(capi.CCA_WS_FORWARD, B, Cq, C, H, W, dt)
+        ws = torch.empty((max(nws, 16),), dtype=torch.uint8, device=q.device)
+        rc = lib.cca_b200_forward(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(),
+                                  ws.data_ptr(), ws.numel(), B, Cq, C, H, W, dt, _IMPL_FLAGS[impl],
+                                  _stream_ptr(q.device))
+    capi.check(rc, "cca_b200_forward")
+    return out, lse
+
+
+def cca_backward(dout, q, k, v, out, lse, impl: str = "auto"):
+    """Gradients (dq, dk, dv) of ``cca_forward`` given dout and the saved forward tensors."""
+    _check_inputs(q, k, v)
+    lib = capi.load()
+    dout, q, k, v, out = (t.contiguous() for t in (dout, q, k, v, out))
+    if dout.dtype != q.dtype or out.dtype != q.dtype or dout.shape != v.shape or out.shape != v.shape:
+        raise RuntimeError("ccnet_b200: dout/out must match v in shape and dtype")
+    lse = lse.contiguous()
+    B, Cq, H, W = q.shape
+    C = v.shape[1]
+    dt = _DTYPES[q.dtype]
+    with torch.cuda.device(q.device):
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        nws = lib.cca_b200_workspace_bytes(capi.CCA_WS_BACKWARD, B, Cq, C, H, W, dt)
+        ws = torch.empty((max(nws, 16),), dtype=torch.uint8, device=q.device)
+        rc = lib.cca_b200_backward(dout.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+                                   lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                   ws.data_ptr(), ws.numel(), B, Cq, C, H, W, dt, _IMPL_FLAGS[impl],
+                                   _stream_ptr(q.device))
+    capi.check(rc, "cca_b200_backward")
+    return dq, dk, dv
+
+
+class _CCAFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, impl):
+        out, lse = cca_forward(q, k, v, impl)
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.impl = impl
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, out, lse = ctx.saved_tensors
+        bimpl = "auto" if ctx.impl == "tc" else ctx.impl
+        dq, dk, dv = cca_backward(dout, q, k, v, out, lse, bimpl)
+        return dq, dk, dv, None
+
+
+def cca(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, impl: str = "auto") -> torch.Tensor:
+    """Differentiable criss-cross attention step (out only)."""
+    return _CCAFunction.apply(q, k, v, impl)

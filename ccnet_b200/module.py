@@ -1,0 +1,54 @@
+"""Drop-in ``CrissCrossAttention`` nn.Module (mirror of cc_attention/functions.py:15-49).
+
+Same constructor, parameter names/shapes/init and forward signature as the reference, so
+``networks/ccnet.py:13`` (``from cc_attention import CrissCrossAttention``) and released
+checkpoints (``head.cca.*`` keys) work unchanged.  The 1x1 projections stay stock torch
+convs (north_star); everything between them and the residual is the CUDA extension.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .functional import cca
+
+
+class CrissCrossAttention(nn.Module):
+    """Criss-Cross Attention Module (B200-native operator behind the reference surface)."""
+
+    def __init__(self, in_dim: int, impl: str = "auto"):
+        super().__init__()
+        self.query_conv = nn.Conv2d(in_channels=in_dim, out_channels=in_dim // 8, kernel_size=1)  # functions.py:19
+        self.key_conv = nn.Conv2d(in_channels=in_dim, out_channels=in_dim // 8, kernel_size=1)    # functions.py:20
+        self.value_conv = nn.Conv2d(in_channels=in_dim, out_channels=in_dim, kernel_size=1)       # functions.py:21
+        self.softmax = nn.Softmax(dim=3)      # kept for attribute parity (functions.py:22); fused in the kernel
+        self.INF = None                       # functions.py:23 -- the mask is a predicate inside the kernel
+        self.gamma = nn.Parameter(torch.zeros(1))                                                  # functions.py:24
+        self.impl = impl
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("ccnet_b200.CrissCrossAttention runs on CUDA (B200) only; "
+                               "the CPU restatement lives in oracle/ and is test-only")
+        q = self.query_conv(x)                # functions.py:29
+        k = self.key_conv(x)                  # functions.py:32
+        v = self.value_conv(x)                # functions.py:35
+        if q.dtype != v.dtype or k.dtype != v.dtype:       # autocast corner: keep one dtype
+            q, k = q.to(v.dtype), k.to(v.dtype)
+        o = cca(q, k, v, self.impl)           # functions.py:30-47 fused
+        return self.gamma * o + x             # functions.py:49
+
+
+class RCCA(nn.Module):
+    """The recurrence of networks/ccnet.py:116-119: the same CCA module applied R times."""
+
+    def __init__(self, in_dim: int, recurrence: int = 2, impl: str = "auto"):
+        super().__init__()
+        self.cca = CrissCrossAttention(in_dim, impl)
+        self.recurrence = recurrence
+
+    def forward(self, x):
+        out = x
+        for _ in range(self.recurrence):
+            out = self.cca(out)
+        return out

@@ -1,0 +1,117 @@
+/*
+ * cca_b200.h -- C ABI of the B200-native criss-cross attention operator.
+ *
+ * This is the drop-in boundary for CCNet's hot path.  The reference exposes the path
+ * only as a Python nn.Module (cc_attention/functions.py:15-49; the mounted branch has
+ * no native FFI -- SURVEY.md F1), so the entry points below are what a binding for that
+ * module binds: one call per recurrence step for forward (replaces functions.py:30-47:
+ * the six layout copies, INF mask, two QK^T bmm, cat+softmax, two A.V bmm) and one for
+ * its backward (replaces the autograd graph of those lines).
+ * The 1x1 Q/K/V projections (functions.py:29,32,35) and the gamma*o+x residual
+ * (functions.py:49) stay with the caller, exactly where the reference has them.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types.
+ *   - tensors are NCHW-contiguous, same dtype for q,k,v,out (CCA_F32 or CCA_BF16);
+ *     lse / stats / delta are always fp32.
+ *   - q,k: [B,Cq,H,W]   v,out,dout,dv: [B,C,H,W]   lse: [B,H,W].
+ *   - "device" entry points take device pointers valid on the current CUDA device and a
+ *     cudaStream_t (as void*); they enqueue work and return without synchronising.
+ *   - "host" entry points take host pointers, do H2D, compute, D2H and synchronise.
+ *   - every function returns CCA_OK (0) or a negative cca_status; the message of the
+ *     last failure on the calling thread is available from cca_b200_last_error().
+ *   - inputs are never written; outputs need no initialisation.
+ *   - re-entrant: no global scratch; the caller supplies the (small) workspace.
+ */
+#ifndef CCA_B200_H_
+#define CCA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCA_B200_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define CCA_API __attribute__((visibility("default")))
+#else
+#define CCA_API
+#endif
+
+typedef enum cca_dtype {
+    CCA_F32 = 0,  /* float32 I/O, fp32 accumulate                                       */
+    CCA_BF16 = 1  /* bfloat16 I/O, fp32 accumulate, fp32 lse                            */
+} cca_dtype;
+
+typedef enum cca_status {
+    CCA_OK = 0,
+    CCA_ERR_INVALID = -1,      /* bad pointer / shape / dtype / flags                    */
+    CCA_ERR_UNSUPPORTED = -2,  /* shape outside what the kernels cover (see limits)      */
+    CCA_ERR_WORKSPACE = -3,    /* workspace too small                                    */
+    CCA_ERR_CUDA = -4,         /* CUDA runtime error (message in cca_b200_last_error)    */
+    CCA_ERR_DEVICE = -5        /* current device is not sm_100                           */
+} cca_status;
+
+/* flags (bit mask) */
+#define CCA_FLAG_AUTO 0u        /* pick the fastest kernel family that covers the shape  */
+#define CCA_FLAG_FORCE_SIMT 1u  /* generic CUDA-core kernels (any shape within limits)   */
+#define CCA_FLAG_FORCE_TC 2u    /* tcgen05 tensor-core kernels; error if not applicable  */
+
+/* which workspace */
+#define CCA_WS_FORWARD 0
+#define CCA_WS_BACKWARD 1
+
+CCA_API int cca_b200_version(void);
+CCA_API const char *cca_b200_last_error(void);
+CCA_API const char *cca_b200_strerror(int status);
+
+/* 1 if the current CUDA device can run this library (compute capability 10.x), else 0;
+ * negative cca_status on CUDA failure. */
+CCA_API int cca_b200_device_ok(void);
+
+/* Number of kernels this library has launched in this process so far (for audits). */
+CCA_API unsigned long long cca_b200_launch_count(void);
+
+/* Bytes of device workspace the forward / backward call needs for this problem. */
+CCA_API size_t cca_b200_workspace_bytes(int which, int B, int Cq, int C, int H, int W, int dtype);
+
+/*
+ * One criss-cross attention step, forward (replaces functions.py:30-47):
+ *   e_col[b,h,w,g] = <q[b,:,h,w], k[b,:,g,w]>   (-inf at g == h)
+ *   e_row[b,h,w,g] = <q[b,:,h,w], k[b,:,h,g]>
+ *   a = softmax over the H+W entries;  out = a_col . v(column) + a_row . v(row)
+ *   lse[b,h,w] = logsumexp of the H+W logits (saved for backward).
+ */
+CCA_API int cca_b200_forward(const void *q, const void *k, const void *v, void *out, float *lse,
+                     void *workspace, size_t workspace_bytes,
+                     int B, int Cq, int C, int H, int W, int dtype, unsigned flags,
+                     void *cuda_stream);
+
+/*
+ * Backward of the step above: given dout = dL/dout, and the forward's q,k,v,out,lse,
+ * writes dq, dk, dv (closed form; the attention matrix is recomputed, never stored).
+ */
+CCA_API int cca_b200_backward(const void *dout, const void *q, const void *k, const void *v,
+                      const void *out, const float *lse, void *dq, void *dk, void *dv,
+                      void *workspace, size_t workspace_bytes,
+                      int B, int Cq, int C, int H, int W, int dtype, unsigned flags,
+                      void *cuda_stream);
+
+/*
+ * Host-buffer variants: same maths, pointers are HOST memory (pinned or pageable).
+ * They allocate device memory, copy in, run on an internal stream, copy out, free and
+ * synchronise.  These are the calls a non-CUDA host language binds directly.
+ */
+CCA_API int cca_b200_forward_host(const void *q, const void *k, const void *v, void *out, float *lse,
+                          int B, int Cq, int C, int H, int W, int dtype, unsigned flags);
+CCA_API int cca_b200_backward_host(const void *dout, const void *q, const void *k, const void *v,
+                           const void *out, const float *lse, void *dq, void *dk, void *dv,
+                           int B, int Cq, int C, int H, int W, int dtype, unsigned flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCA_B200_H_ */

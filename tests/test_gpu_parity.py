@@ -1,0 +1,216 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).  Every call goes through the C ABI
+(ccnet_b200.functional -> ctypes -> libcca_b200.so); the oracle is only the checker.
+
+Tolerances (BASELINE.json north_star): fp32 max-abs <= 1e-3 on identical Q/K/V; bf16 <= 1e-2
+against the fp32 oracle evaluated on the bf16-rounded Q/K/V."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-3
+BF16_TOL = 1e-2
+
+IMPLS = ["simt", "auto"]
+
+
+def _dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _oracle():
+    from oracle import cca_oracle
+    return cca_oracle
+
+
+def _rand_qkv(B, Cq, C, H, W, seed, scale=1.0, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    q = (torch.randn(B, Cq, H, W, generator=g) * scale).to(dtype)
+    k = (torch.randn(B, Cq, H, W, generator=g) * scale).to(dtype)
+    v = torch.randn(B, C, H, W, generator=g).to(dtype)
+    return q, k, v
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_forward_vs_golden_reference_outputs(golden, impl):
+    """Identical Q/K/V as the reference module produced; compare with the reference's own O."""
+    from ccnet_b200 import cca_forward
+    dev = _dev()
+    q, k, v = (torch.from_numpy(golden[n]).to(dev) for n in "qkv")
+    out, lse = cca_forward(q, k, v, impl=impl)
+    ref = torch.from_numpy(golden["o64"]).to(dev)
+    assert torch.isfinite(out).all() and torch.isfinite(lse).all()
+    err = (out.double() - ref).abs().max().item()
+    assert err <= FP32_TOL, (golden["name"], err)
+    assert err <= 5e-5 * max(1.0, ref.abs().max().item()), (golden["name"], err)   # SIMT/3xbf16 are ~fp32 exact
+
+
+SHAPES = [
+    # B, Cq, C, H, W
+    (2, 8, 64, 5, 6), (1, 8, 64, 32, 32), (2, 4, 32, 9, 7), (1, 2, 16, 1, 11), (1, 2, 16, 13, 1),
+    (1, 1, 8, 1, 1), (1, 16, 128, 17, 33), (1, 64, 512, 97, 97), (2, 64, 512, 65, 65), (1, 7, 19, 40, 70),
+    (1, 8, 48, 130, 150),
+]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("shape", SHAPES)
+def test_forward_fp32_vs_oracle(shape, impl):
+    from ccnet_b200 import cca_forward
+    O = _oracle()
+    dev = _dev()
+    q, k, v = _rand_qkv(*shape, seed=sum(shape))
+    out, lse = cca_forward(q.to(dev), k.to(dev), v.to(dev), impl=impl)
+    ro, rl = O.cca_forward(q.double(), k.double(), v.double())
+    assert (out.cpu().double() - ro).abs().max().item() <= FP32_TOL
+    assert (lse.cpu().double() - rl).abs().max().item() <= FP32_TOL
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("shape", [(2, 8, 64, 5, 6), (1, 16, 128, 17, 33), (1, 64, 512, 97, 97), (1, 2, 16, 1, 11)])
+def test_forward_bf16_vs_oracle_on_rounded_inputs(shape, impl):
+    from ccnet_b200 import cca_forward
+    O = _oracle()
+    dev = _dev()
+    q, k, v = _rand_qkv(*shape, seed=7 + sum(shape), scale=0.6, dtype=torch.bfloat16)
+    out, lse = cca_forward(q.to(dev), k.to(dev), v.to(dev), impl=impl)
+    assert out.dtype == torch.bfloat16 and lse.dtype == torch.float32
+    ro, rl = O.cca_forward(q.double(), k.double(), v.double())
+    scale = max(1.0, ro.abs().max().item())
+    assert (out.cpu().double() - ro).abs().max().item() <= BF16_TOL * scale
+    assert (lse.cpu().double() - rl).abs().max().item() <= BF16_TOL
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 64, 5, 6), (2, 4, 32, 9, 7), (1, 2, 16, 1, 11), (1, 2, 16, 13, 1), (1, 1, 8, 1, 1),
+                                   (1, 16, 128, 17, 33), (1, 64, 512, 65, 65), (1, 8, 48, 130, 150)])
+def test_backward_fp32_vs_oracle(shape):
+    from ccnet_b200 import cca_backward, cca_forward
+    O = _oracle()
+    dev = _dev()
+    q, k, v = _rand_qkv(*shape, seed=11 + sum(shape), scale=0.7)
+    g = torch.Generator().manual_seed(99)
+    dout = torch.randn(v.shape, generator=g)
+    out, lse = cca_forward(q.to(dev), k.to(dev), v.to(dev))
+    dq, dk, dv = cca_backward(dout.to(dev), q.to(dev), k.to(dev), v.to(dev), out, lse)
+    rq, rk, rv = O.cca_backward(dout.double(), q.double(), k.double(), v.double())
+    for got, ref, name in ((dq, rq, "dq"), (dk, rk, "dk"), (dv, rv, "dv")):
+        tol = FP32_TOL * max(1.0, ref.abs().max().item())
+        assert (got.cpu().double() - ref).abs().max().item() <= tol, name
+
+
+def test_backward_bf16_vs_oracle():
+    from ccnet_b200 import cca_backward, cca_forward
+    O = _oracle()
+    dev = _dev()
+    q, k, v = _rand_qkv(2, 8, 64, 12, 10, seed=5, scale=0.6, dtype=torch.bfloat16)
+    dout = torch.randn(v.shape, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16)
+    out, lse = cca_forward(q.to(dev), k.to(dev), v.to(dev))
+    dq, dk, dv = cca_backward(dout.to(dev), q.to(dev), k.to(dev), v.to(dev), out, lse)
+    rq, rk, rv = O.cca_backward(dout.double(), q.double(), k.double(), v.double())
+    for got, ref in ((dq, rq), (dk, rk), (dv, rv)):
+        assert (got.cpu().double() - ref).abs().max().item() <= 3 * BF16_TOL * max(1.0, ref.abs().max().item())
+
+
+def test_module_vs_golden_fwd_bwd(golden):
+    """x -> y through the drop-in nn.Module, R recurrences, with the reference's parameters."""
+    import cc_attention
+    dev = _dev()
+    x = torch.from_numpy(golden["x"]).to(dev).requires_grad_(True)
+    m = cc_attention.CrissCrossAttention(x.shape[1]).to(dev)
+    m.load_state_dict({n[2:]: torch.from_numpy(a) for n, a in golden.items() if n.startswith("p_")})
+    y = x
+    for _ in range(int(golden["R"])):
+        y = m(y)
+    (y * torch.from_numpy(golden["g"]).to(dev)).sum().backward()
+    torch.backends.cudnn.allow_tf32 = False
+    assert (y.detach().cpu() - torch.from_numpy(golden["y"])).abs().max().item() <= FP32_TOL
+    assert (x.grad.cpu() - torch.from_numpy(golden["dx"])).abs().max().item() <= FP32_TOL * max(
+        1.0, float(np.abs(golden["dx"]).max()))
+    for n, p in m.named_parameters():
+        ref = torch.from_numpy(golden["d_" + n])
+        tol = 2e-3 * max(1.0, ref.abs().max().item())
+        assert (p.grad.cpu() - ref).abs().max().item() <= tol, n
+
+
+def test_full_size_properties_and_oracle_c2():
+    """BASELINE config 2 (B=8, C=512, 97x97): size-independent properties + oracle on 2 samples."""
+    from ccnet_b200 import cca_forward
+    O = _oracle()
+    dev = _dev()
+    torch.manual_seed(0)
+    B, Cq, C, H, W = 8, 64, 512, 97, 97
+    q = torch.randn(B, Cq, H, W, device=dev) * 0.58
+    k = torch.randn(B, Cq, H, W, device=dev) * 0.58
+    v1 = torch.randn(B, C, H, W, device=dev)
+    v2 = torch.randn(B, C, H, W, device=dev)
+    o1, lse = cca_forward(q, k, v1)
+    o2, _ = cca_forward(q, k, v2)
+    o12, _ = cca_forward(q, k, v1 + 2.0 * v2)
+    assert (o12 - (o1 + 2.0 * o2)).abs().max().item() <= 1e-4            # linear in v
+    ones, _ = cca_forward(q, k, torch.ones_like(v1))
+    assert (ones - 1.0).abs().max().item() <= 1e-5                       # attention rows sum to 1
+    # oracle on samples 0 and 7
+    for b in (0, 7):
+        ro, rl = O.cca_forward(q[b:b + 1].cpu().double(), k[b:b + 1].cpu().double(), v1[b:b + 1].cpu().double())
+        assert (o1[b:b + 1].cpu().double() - ro).abs().max().item() <= FP32_TOL
+        assert (lse[b:b + 1].cpu().double() - rl).abs().max().item() <= FP32_TOL
+    # per-sample independence: permuting the batch permutes the output
+    perm = torch.tensor([3, 0, 7, 1, 2, 6, 5, 4], device=dev)
+    op, _ = cca_forward(q[perm], k[perm], v1[perm])
+    assert torch.equal(op, o1[perm])
+
+
+def test_host_buffer_entry_point():
+    """cca_b200_forward_host / backward_host: plain host pointers through the C ABI."""
+    from ccnet_b200 import capi
+    O = _oracle()
+    _dev()
+    lib = capi.load()
+    B, Cq, C, H, W = 2, 4, 24, 7, 9
+    q, k, v = _rand_qkv(B, Cq, C, H, W, seed=42)
+    qn, kn, vn = (np.ascontiguousarray(t.numpy()) for t in (q, k, v))
+    out = np.empty((B, C, H, W), np.float32)
+    lse = np.empty((B, H, W), np.float32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = lib.cca_b200_forward_host(p(qn), p(kn), p(vn), p(out), p(lse), B, Cq, C, H, W, capi.CCA_F32, 0)
+    capi.check(rc, "forward_host")
+    ro, rl = O.cca_forward(q.double(), k.double(), v.double())
+    assert np.abs(out - ro.numpy()).max() <= FP32_TOL and np.abs(lse - rl.numpy()).max() <= FP32_TOL
+    dout = np.random.default_rng(0).standard_normal((B, C, H, W)).astype(np.float32)
+    dq, dk, dv = np.empty_like(qn), np.empty_like(kn), np.empty_like(vn)
+    rc = lib.cca_b200_backward_host(p(dout), p(qn), p(kn), p(vn), p(out), p(lse), p(dq), p(dk), p(dv),
+                                    B, Cq, C, H, W, capi.CCA_F32, 0)
+    capi.check(rc, "backward_host")
+    rq, rk, rv = O.cca_backward(torch.from_numpy(dout).double(), q.double(), k.double(), v.double())
+    for got, ref in ((dq, rq), (dk, rk), (dv, rv)):
+        assert np.abs(got - ref.numpy()).max() <= FP32_TOL * max(1.0, ref.abs().max().item())
+
+
+def test_error_behaviour_on_gpu():
+    from ccnet_b200 import cca_forward
+    dev = _dev()
+    q = torch.randn(1, 4, 5, 5, device=dev)
+    with pytest.raises(RuntimeError):
+        cca_forward(q, q[:, :, :4], torch.randn(1, 8, 5, 5, device=dev))           # shape mismatch
+    with pytest.raises(RuntimeError):
+        cca_forward(q, q, torch.randn(1, 8, 5, 5, device=dev, dtype=torch.float16).float().half())  # dtype
+    with pytest.raises(RuntimeError, match="unsupported|too large"):
+        big = torch.zeros(1, 1, 1, 5000, device=dev)
+        cca_forward(big, big, big)
+
+
+def test_noncontiguous_inputs_and_fresh_output():
+    from ccnet_b200 import cca_forward
+    O = _oracle()
+    dev = _dev()
+    q, k, v = _rand_qkv(1, 4, 16, 6, 8, seed=1)
+    qd = q.to(dev).permute(0, 1, 3, 2).contiguous().permute(0, 1, 3, 2)     # channels/space strided view
+    vd = v.to(dev).to(memory_format=torch.channels_last)
+    out, _ = cca_forward(qd, k.to(dev), vd)
+    ro, _ = O.cca_forward(q.double(), k.double(), v.double())
+    assert (out.cpu().double() - ro).abs().max().item() <= FP32_TOL
+    assert out.data_ptr() != vd.data_ptr()
