@@ -119,6 +119,8 @@ def test_module_vs_golden_fwd_bwd(golden):
     """x -> y through the drop-in nn.Module, R recurrences, with the reference's parameters."""
     import cc_attention
     dev = _dev()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     x = torch.from_numpy(golden["x"]).to(dev).requires_grad_(True)
     m = cc_attention.CrissCrossAttention(x.shape[1]).to(dev)
     m.load_state_dict({n[2:]: torch.from_numpy(a) for n, a in golden.items() if n.startswith("p_")})
@@ -126,7 +128,6 @@ def test_module_vs_golden_fwd_bwd(golden):
     for _ in range(int(golden["R"])):
         y = m(y)
     (y * torch.from_numpy(golden["g"]).to(dev)).sum().backward()
-    torch.backends.cudnn.allow_tf32 = False
     assert (y.detach().cpu() - torch.from_numpy(golden["y"])).abs().max().item() <= FP32_TOL
     assert (x.grad.cpu() - torch.from_numpy(golden["dx"])).abs().max().item() <= FP32_TOL * max(
         1.0, float(np.abs(golden["dx"]).max()))
