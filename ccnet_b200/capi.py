@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcca_b200.so")
 
 CCA_F32, CCA_BF16 = 0, 1
-CCA_FLAG_AUTO, CCA_FLAG_FORCE_SIMT, CCA_FLAG_FORCE_TC = 0, 1, 2
+CCA_FLAG_AUTO, CCA_FLAG_FORCE_SIMT, CCA_FLAG_FORCE_TC, CCA_FLAG_NHWC = 0, 1, 2, 4
 CCA_WS_FORWARD, CCA_WS_BACKWARD = 0, 1
 
 # every symbol include/cca_b200.h declares: name -> (restype, argtypes)
@@ -24,6 +24,7 @@ SYMBOLS = {
     "cca_b200_strerror": (ctypes.c_char_p, [_i]),
     "cca_b200_device_ok": (_i, []),
     "cca_b200_launch_count": (ctypes.c_ulonglong, []),
+    "cca_b200_tc_supported": (_i, [_i] * 6),
     "cca_b200_workspace_bytes": (_sz, [_i] * 7),
     "cca_b200_forward": (_i, [_vp] * 6 + [_sz] + [_i] * 6 + [_u, _vp]),
     "cca_b200_backward": (_i, [_vp] * 10 + [_sz] + [_i] * 6 + [_u, _vp]),

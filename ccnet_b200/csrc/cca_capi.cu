@@ -40,6 +40,8 @@ using namespace cca;
 extern "C" {
 
 int cca_b200_version(void) { return CCA_B200_VERSION; }
+// profiling aid (not declared in the public header): device buffer of 2 x 4 x 512 int64 clock stamps
+CCA_API void cca_b200__set_debug_buffer(void *p) { set_tc_debug_buffer(p); }
 const char *cca_b200_last_error(void) { return g_err; }
 const char *cca_b200_strerror(int s)
 {
@@ -65,6 +67,12 @@ int cca_b200_device_ok(void)
     return major == 10 ? 1 : 0;
 }
 
+int cca_b200_tc_supported(int B, int Cq, int C, int H, int W, int dtype)
+{
+    if (check_dims(B, Cq, C, H, W, dtype)) return 0;
+    return tc_forward_supported(Dims{B, Cq, C, H, W}, dtype) ? 1 : 0;
+}
+
 size_t cca_b200_workspace_bytes(int which, int B, int Cq, int C, int H, int W, int dtype)
 {
     (void)Cq; (void)C; (void)dtype;
@@ -86,14 +94,19 @@ int cca_b200_forward(const void *q, const void *k, const void *v, void *out, flo
     const Dims d{B, Cq, C, H, W};
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const char *why = "";
-    const bool tc_ok = tc_forward_supported(d, dtype);
-    if (flags & CCA_FLAG_FORCE_TC) {
-        if (!tc_ok) return fail(CCA_ERR_UNSUPPORTED, "tensor-core forward does not cover this shape%s%s");
-    }
+    const bool nhwc = (flags & CCA_FLAG_NHWC) != 0;
+    const bool tc_ok = nhwc && tc_forward_supported(d, dtype);
+    if ((flags & CCA_FLAG_FORCE_TC) && !tc_ok)
+        return fail(CCA_ERR_UNSUPPORTED, "tensor-core forward needs CCA_FLAG_NHWC and a covered shape%s%s");
+    if (nhwc && (!tc_ok || (flags & CCA_FLAG_FORCE_SIMT)))
+        return fail(CCA_ERR_UNSUPPORTED, "channels-last tensors are only handled by the tensor-core kernels; pass NCHW%s%s");
     cudaError_t e;
-    if (tc_ok && !(flags & CCA_FLAG_FORCE_SIMT)) {
+    if (tc_ok) {
+        if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+             reinterpret_cast<uintptr_t>(out)) & 15)
+            return fail(CCA_ERR_INVALID, "tensor-core path needs 16-byte aligned tensors%s%s");
         e = tc_forward(q, k, v, out, lse, ws, d, dtype, st, &why);
-        if (e != cudaSuccess) return cuda_fail(e, "tc_forward");
+        if (e != cudaSuccess) return cuda_fail(e, why && *why ? why : "tc_forward");
         return CCA_OK;
     }
     if (!simt_supported(d, false)) return fail(CCA_ERR_UNSUPPORTED, "H or W too large for the generic kernels%s%s");
@@ -112,7 +125,8 @@ int cca_b200_backward(const void *dout, const void *q, const void *k, const void
         return fail(CCA_ERR_INVALID, "null pointer%s%s");
     if (ws_bytes < cca_b200_workspace_bytes(CCA_WS_BACKWARD, B, Cq, C, H, W, dtype))
         return fail(CCA_ERR_WORKSPACE, "backward workspace too small%s%s");
-    if (flags & CCA_FLAG_FORCE_TC) return fail(CCA_ERR_UNSUPPORTED, "tensor-core backward not available%s%s");
+    if (flags & (CCA_FLAG_FORCE_TC | CCA_FLAG_NHWC))
+        return fail(CCA_ERR_UNSUPPORTED, "backward: tensor-core / channels-last path not available; pass NCHW%s%s");
     const Dims d{B, Cq, C, H, W};
     if (!simt_supported(d, true)) return fail(CCA_ERR_UNSUPPORTED, "H or W too large for the generic kernels%s%s");
     const char *why = "";

@@ -44,5 +44,6 @@ cudaError_t tc_forward(const void *q, const void *k, const void *v, void *out, f
                        Dims d, int dtype, cudaStream_t st, const char **why);
 
 void count_launch(int n = 1);
+void set_tc_debug_buffer(void *p);
 
 }  // namespace cca

@@ -32,21 +32,44 @@ def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+def tc_eligible(B: int, Cq: int, C: int, H: int, W: int, dtype: torch.dtype) -> bool:
+    """True if the tcgen05 (channels-last) forward kernels cover this problem."""
+    if dtype not in _DTYPES:
+        return False
+    return capi.load().cca_b200_tc_supported(B, Cq, C, H, W, _DTYPES[dtype]) == 1
+
+
 def cca_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, impl: str = "auto"):
-    """One criss-cross step: returns (out[B,C,H,W], lse[B,H,W] fp32)."""
+    """One criss-cross step: returns (out[B,C,H,W], lse[B,H,W] fp32).
+
+    ``impl``: "auto" (tensor-core kernels when they cover the shape, else the generic kernels),
+    "tc" (tensor-core kernels or error), "simt" (generic kernels).  The tensor-core kernels work on
+    channels-last memory (logical shape unchanged); inputs in another memory format are converted and
+    the output is returned channels-last.  The generic kernels work on NCHW-contiguous memory.
+    """
     _check_inputs(q, k, v)
     lib = capi.load()
-    q, k, v = q.contiguous(), k.contiguous(), v.contiguous()   # reference calls .contiguous() too
     B, Cq, H, W = q.shape
     C = v.shape[1]
     dt = _DTYPES[q.dtype]
+    flags = _IMPL_FLAGS[impl]
+    use_tc = impl in ("auto", "tc") and lib.cca_b200_tc_supported(B, Cq, C, H, W, dt) == 1
+    if impl == "tc" and not use_tc:
+        raise RuntimeError(f"ccnet_b200: tensor-core kernels do not cover q{tuple(q.shape)} v{tuple(v.shape)} {q.dtype}")
+    if use_tc:
+        fmt = torch.channels_last
+        q, k, v = (t.contiguous(memory_format=fmt) for t in (q, k, v))
+        flags |= capi.CCA_FLAG_NHWC
+    else:
+        fmt = torch.contiguous_format
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()   # reference calls .contiguous() too
     with torch.cuda.device(q.device):
-        out = torch.empty_like(v)
+        out = torch.empty_like(v, memory_format=fmt)
         lse = torch.empty((B, H, W), dtype=torch.float32, device=q.device)
         nws = lib.cca_b200_workspace_bytes(capi.CCA_WS_FORWARD, B, Cq, C, H, W, dt)
         ws = torch.empty((max(nws, 16),), dtype=torch.uint8, device=q.device)
         rc = lib.cca_b200_forward(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(),
-                                  ws.data_ptr(), ws.numel(), B, Cq, C, H, W, dt, _IMPL_FLAGS[impl],
+                                  ws.data_ptr(), ws.numel(), B, Cq, C, H, W, dt, flags,
                                   _stream_ptr(q.device))
     capi.check(rc, "cca_b200_forward")
     return out, lse
@@ -69,7 +92,8 @@ def cca_backward(dout, q, k, v, out, lse, impl: str = "auto"):
         ws = torch.empty((max(nws, 16),), dtype=torch.uint8, device=q.device)
         rc = lib.cca_b200_backward(dout.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
                                    lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
-                                   ws.data_ptr(), ws.numel(), B, Cq, C, H, W, dt, _IMPL_FLAGS[impl],
+                                   ws.data_ptr(), ws.numel(), B, Cq, C, H, W, dt,
+                                   capi.CCA_FLAG_FORCE_SIMT if impl == "simt" else capi.CCA_FLAG_AUTO,
                                    _stream_ptr(q.device))
     capi.check(rc, "cca_b200_backward")
     return dq, dk, dv

@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .functional import cca
+from .functional import cca, tc_eligible
 
 
 class CrissCrossAttention(nn.Module):
@@ -30,6 +30,11 @@ class CrissCrossAttention(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("ccnet_b200.CrissCrossAttention runs on CUDA (B200) only; "
                                "the CPU restatement lives in oracle/ and is test-only")
+        B, C, H, W = x.shape
+        if self.impl != "simt" and tc_eligible(B, C // 8, C, H, W, x.dtype):
+            # tensor-core kernels are channels-last; converting x once makes the three 1x1 convs emit
+            # channels-last q/k/v directly (no-op when the surrounding network already is channels_last)
+            x = x.contiguous(memory_format=torch.channels_last)
         q = self.query_conv(x)                # functions.py:29
         k = self.key_conv(x)                  # functions.py:32
         v = self.value_conv(x)                # functions.py:35

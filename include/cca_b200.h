@@ -12,8 +12,8 @@
  *
  * Conventions
  *   - plain pointers and sizes only; no torch / C++ types.
- *   - tensors are NCHW-contiguous, same dtype for q,k,v,out (CCA_F32 or CCA_BF16);
- *     lse / stats / delta are always fp32.
+ *   - tensors are NCHW-contiguous (default) or channels-last (CCA_FLAG_NHWC), same dtype
+ *     for q,k,v,out (CCA_F32 or CCA_BF16); lse / stats / delta are always fp32 [B,H,W].
  *   - q,k: [B,Cq,H,W]   v,out,dout,dv: [B,C,H,W]   lse: [B,H,W].
  *   - "device" entry points take device pointers valid on the current CUDA device and a
  *     cudaStream_t (as void*); they enqueue work and return without synchronising.
@@ -59,6 +59,12 @@ typedef enum cca_status {
 #define CCA_FLAG_AUTO 0u        /* pick the fastest kernel family that covers the shape  */
 #define CCA_FLAG_FORCE_SIMT 1u  /* generic CUDA-core kernels (any shape within limits)   */
 #define CCA_FLAG_FORCE_TC 2u    /* tcgen05 tensor-core kernels; error if not applicable  */
+#define CCA_FLAG_NHWC 4u        /* tensors are channels-last: q,k [B,H,W,Cq]; v,out,dout,dq.. [B,H,W,C]
+                                 * (torch.channels_last of the same logical NCHW shape).  This is the
+                                 * layout of the tensor-core kernels: rows and columns of the image are
+                                 * both "L pixels with contiguous channels", so TMA boxes and UMMA operand
+                                 * tiles serve the two branches symmetrically.  Without the flag tensors
+                                 * are NCHW-contiguous and the generic kernels run.                      */
 
 /* which workspace */
 #define CCA_WS_FORWARD 0
@@ -74,6 +80,9 @@ CCA_API int cca_b200_device_ok(void);
 
 /* Number of kernels this library has launched in this process so far (for audits). */
 CCA_API unsigned long long cca_b200_launch_count(void);
+
+/* 1 if the tensor-core (tcgen05) forward covers this problem in NHWC layout, else 0. */
+CCA_API int cca_b200_tc_supported(int B, int Cq, int C, int H, int W, int dtype);
 
 /* Bytes of device workspace the forward / backward call needs for this problem. */
 CCA_API size_t cca_b200_workspace_bytes(int which, int B, int Cq, int C, int H, int W, int dtype);

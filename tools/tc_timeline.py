@@ -1,0 +1,29 @@
+"""Dump the per-role clock64 timeline of CTA 0 of the tcgen05 forward kernel (profiling aid)."""
+import ctypes, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from ccnet_b200 import capi, cca_forward
+lib = capi.load()
+dev = torch.device("cuda:0")
+B, Cq, C, H, W = 8, 64, 512, 97, 97
+q = torch.randn(B, Cq, H, W, device=dev).contiguous(memory_format=torch.channels_last)
+k = torch.randn(B, Cq, H, W, device=dev).contiguous(memory_format=torch.channels_last)
+v = torch.randn(B, C, H, W, device=dev).contiguous(memory_format=torch.channels_last)
+for _ in range(3):
+    cca_forward(q, k, v, impl="tc")
+buf = torch.zeros(2 * 4 * 512, dtype=torch.int64, device=dev)
+fn = lib.cca_b200__set_debug_buffer
+fn.argtypes = [ctypes.c_void_p]; fn.restype = None
+fn(buf.data_ptr())
+cca_forward(q, k, v, impl="tc")
+torch.cuda.synchronize()
+fn(None)
+t = buf.cpu().view(2, 4, 512)
+names = ["producer(slot free->issue)", "converter(full, op_empty, done)", "mma", "softmax/epilogue"]
+for ps, pname in enumerate(["COLUMN pass", "ROW pass"]):
+    base = min(int(x) for x in t[ps].flatten() if x > 0)
+    print("=====", pname)
+    for role in range(4):
+        st = [int(x) - base for x in t[ps, role] if x > 0]
+        print(f"--- {names[role]}: {len(st)} stamps")
+        print(" ".join(str(x) for x in st[:70]))
