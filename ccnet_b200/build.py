@@ -14,8 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libcca_b200.so")
-SOURCES = ["cca_capi.cu", "cca_simt.cu", "cca_tc_fwd.cu"]
-HEADERS = ["cca_common.cuh", "../../include/cca_b200.h"]
+SOURCES = ["cca_capi.cu", "cca_simt.cu", "cca_tc_fwd.cu", "cca_tc_bwd.cu"]
+HEADERS = ["cca_common.cuh", "cca_sm100.cuh", "cca_tc_common.cuh", "../../include/cca_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo", "--use_fast_math",

@@ -125,11 +125,25 @@ int cca_b200_backward(const void *dout, const void *q, const void *k, const void
         return fail(CCA_ERR_INVALID, "null pointer%s%s");
     if (ws_bytes < cca_b200_workspace_bytes(CCA_WS_BACKWARD, B, Cq, C, H, W, dtype))
         return fail(CCA_ERR_WORKSPACE, "backward workspace too small%s%s");
-    if (flags & (CCA_FLAG_FORCE_TC | CCA_FLAG_NHWC))
-        return fail(CCA_ERR_UNSUPPORTED, "backward: tensor-core / channels-last path not available; pass NCHW%s%s");
     const Dims d{B, Cq, C, H, W};
-    if (!simt_supported(d, true)) return fail(CCA_ERR_UNSUPPORTED, "H or W too large for the generic kernels%s%s");
     const char *why = "";
+    const bool nhwc = (flags & CCA_FLAG_NHWC) != 0;
+    const bool tc_ok = nhwc && tc_backward_supported(d, dtype);
+    if ((flags & CCA_FLAG_FORCE_TC) && !tc_ok)
+        return fail(CCA_ERR_UNSUPPORTED, "tensor-core backward needs CCA_FLAG_NHWC and a covered shape%s%s");
+    if (nhwc && (!tc_ok || (flags & CCA_FLAG_FORCE_SIMT)))
+        return fail(CCA_ERR_UNSUPPORTED, "channels-last tensors are only handled by the tensor-core kernels; pass NCHW%s%s");
+    if (tc_ok) {
+        if ((reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
+             reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(dq) |
+             reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv)) & 15)
+            return fail(CCA_ERR_INVALID, "tensor-core path needs 16-byte aligned tensors%s%s");
+        cudaError_t e = tc_backward(dout, q, k, v, out, lse, dq, dk, dv, ws, d, dtype,
+                                    reinterpret_cast<cudaStream_t>(stream), &why);
+        if (e != cudaSuccess) return cuda_fail(e, why && *why ? why : "tc_backward");
+        return CCA_OK;
+    }
+    if (!simt_supported(d, true)) return fail(CCA_ERR_UNSUPPORTED, "H or W too large for the generic kernels%s%s");
     cudaError_t e = simt_backward(dout, q, k, v, out, lse, dq, dk, dv, ws, d, dtype,
                                   reinterpret_cast<cudaStream_t>(stream), &why);
     if (e != cudaSuccess) return cuda_fail(e, "simt_backward");

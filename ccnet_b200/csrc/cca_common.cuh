@@ -43,6 +43,10 @@ bool tc_forward_supported(Dims d, int dtype);
 cudaError_t tc_forward(const void *q, const void *k, const void *v, void *out, float *lse, void *ws,
                        Dims d, int dtype, cudaStream_t st, const char **why);
 
+bool tc_backward_supported(Dims d, int dtype);
+cudaError_t tc_backward(const void *dout, const void *q, const void *k, const void *v, const void *out, const float *lse,
+                        void *dq, void *dk, void *dv, void *ws, Dims d, int dtype, cudaStream_t st, const char **why);
+
 void count_launch(int n = 1);
 void set_tc_debug_buffer(void *p);
 

@@ -1,0 +1,441 @@
+// tcgen05 / TMA backward kernel of criss-cross attention for sm_100a (channels-last tensors).
+//
+// Closed form of SURVEY.md 8(a) row a11 (autograd of cc_attention/functions.py:38-47), flash-style: the
+// attention matrix is recomputed per line from (q, k, lse), never stored.  As in the forward, a row and a
+// column of a channels-last image are the same object, so one kernel runs twice:
+//   pass 1 (columns, self entry masked): dq, dk, dv  = column-branch contributions
+//   pass 2 (rows)                      : dq, dk, dv += row-branch contributions (partials re-read by TMA)
+// Each line CTA owns all outputs of its line: no atomics, deterministic.
+//
+// Per line (jq = query pixel, jk = key pixel, both < L <= LK):
+//   S  = Q K^T                     (K-dim Cq)        P  = exp(S - lse[jq])            [TMEM -> planes in smem]
+//   dP = dO V^T                    (K-dim C, chunked, accumulated in TMEM over the V/dO chunks)
+//   dV[jk,c] = sum_jq P[jq,jk] dO[jq,c]   per chunk   (A = P planes read MN-major = P^T, B = dO chunk)
+//   dS = P * (dP - delta[jq])      [planes overwrite P]
+//   dQ[jq,c] = sum_jk dS[jq,jk] K[jk,c]   (A = dS planes K-major)     dK[jk,c] = sum_jq dS[jq,jk] Q[jq,c]  (A = dS^T)
+// All GEMMs run as bf16x3 split MMAs (hi*hi + hi*lo + lo*hi) with fp32 accumulation in TMEM.
+// The same operand planes serve several GEMMs: planes over channels are a K-major operand when the
+// contraction runs over channels (S, dP) and an MN-major B operand when channels are the output (dV, dQ, dK);
+// planes over key pixels are K-major A for dQ and MN-major A (= transpose) for dV / dK.
+#include "cca_tc_common.cuh"
+
+namespace cca {
+namespace {
+using namespace tc;
+
+constexpr int kTmemCols = 256;      // S / dP: [0,128)   O0: [128,192)   O1: [192,256)
+
+struct BwdParams {
+    int B, H, W, C, Cq;
+    int L, NL, col;
+    const float *lse;
+    const float *delta;
+};
+
+template <int LK> struct BwdSmem {
+    using T = Tiles<LK>;
+    static constexpr int off_ld = 0;                       // 2 load slots
+    static constexpr int off_out = off_ld + 2 * T::kSlot;  // 2 out slots
+    static constexpr int off_p = off_out + 2 * T::kSlot;   // P / dS planes (hi, lo); over-reads land in op buffers
+    static constexpr int off_op = off_p + T::kP;           // 2 operand buffers
+    static constexpr int off_tail = off_op + 2 * T::kOp;   // 256 B pad for the 16-row over-read of M=128 MMAs
+    static constexpr int off_bar = off_tail + 256;
+    static constexpr int kBytes = off_bar + 256 + 1024;
+};
+
+enum { B_LD_FULL = 0, B_LD_EMPTY = 2, B_OP_FULL = 4, B_OP_EMPTY = 6, B_S_FULL = 8, B_S_EMPTY = 9, B_P_FULL = 10,
+       B_P_EMPTY = 11, B_O_FULL = 12, B_O_EMPTY = 14, B_OUT_FULL = 16, B_DP_FULL = 18, B_DS_FULL = 19, B_COUNT = 20 };
+
+template <int LK>
+__global__ void __launch_bounds__(kThreads, 1)
+cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
+                  const __grid_constant__ CUtensorMap mv, const __grid_constant__ CUtensorMap mdo,
+                  const __grid_constant__ CUtensorMap mdq, const __grid_constant__ CUtensorMap mdk,
+                  const __grid_constant__ CUtensorMap mdv, BwdParams p)
+{
+    using T = Tiles<LK>;
+    using S = BwdSmem<LK>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S::off_bar);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::off_bar + 8 * B_COUNT);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NCH = p.C / kNC;
+    const int KQ = p.Cq / 16;
+    const int NI = 4 + 2 * NCH;               // load items per line: Q K (V dO)* Q K
+    const int NO = NCH + 2;                   // output items per line: dV chunks, dQ, dK
+    const int total_lines = p.B * p.NL;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars[B_LD_FULL + i], 1);            mbar_init(&bars[B_LD_EMPTY + i], kConvThreads);
+            mbar_init(&bars[B_OP_FULL + i], kConvThreads); mbar_init(&bars[B_OP_EMPTY + i], 1);
+            mbar_init(&bars[B_O_FULL + i], 1);             mbar_init(&bars[B_O_EMPTY + i], 128);
+            mbar_init(&bars[B_OUT_FULL + i], 1);
+        }
+        mbar_init(&bars[B_S_FULL], 1);   mbar_init(&bars[B_S_EMPTY], 128);
+        mbar_init(&bars[B_P_FULL], 128); mbar_init(&bars[B_P_EMPTY], 1);
+        mbar_init(&bars[B_DP_FULL], 1);  mbar_init(&bars[B_DS_FULL], 128);
+        fence_mbar_init();
+        prefetch_tmap(&mq); prefetch_tmap(&mk); prefetch_tmap(&mv); prefetch_tmap(&mdo);
+        prefetch_tmap(&mdq); prefetch_tmap(&mdk); prefetch_tmap(&mdv);
+    }
+    if (warp == 0) tmem_alloc<kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    auto line_coords = [&](int line, int &cw, int &ch, int &cb) {
+        cb = line / p.NL;
+        const int i = line - cb * p.NL;
+        if (p.col) { cw = i; ch = 0; } else { cw = 0; ch = i; }
+    };
+
+    if (warp == kWarpProducer) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int line = blockIdx.x; line < total_lines; line += gridDim.x) {
+                int cw, ch, cb;
+                line_coords(line, cw, ch, cb);
+                for (int item = 0; item < NI; ++item, ++g) {
+                    const int slot = g & 1;
+                    mbar_wait(&bars[B_LD_EMPTY + slot], ((g >> 1) & 1) ^ 1);
+                    uint8_t *dst = smem + S::off_ld + slot * T::kSlot;
+                    mbar_expect_tx(&bars[B_LD_FULL + slot], T::kSlot);
+                    const CUtensorMap *m;
+                    int c0 = 0;
+                    if (item < 2 || item >= 2 + 2 * NCH) m = (item & 1) ? &mk : &mq;
+                    else { m = (item & 1) ? &mdo : &mv; c0 = ((item - 2) >> 1) * kNC; }
+                    tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, cb);
+                    tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, cb);
+                }
+            }
+        }
+    } else if (warp == kWarpMma) {
+        // =============================== MMA issuer ===============================
+        const uint32_t id_kk_s = instr_desc(kFmtBF16, kFmtBF16, 128, LK, false, false);    // S, dP : K-major x K-major, N = LK
+        const uint32_t id_mn_mn = instr_desc(kFmtBF16, kFmtBF16, 128, kNC, true, true);    // dV, dK: A^T planes x channel planes
+        const uint32_t id_k_mn = instr_desc(kFmtBF16, kFmtBF16, 128, kNC, false, true);    // dQ
+        const uint32_t op0 = smem_u32(smem + S::off_op), op1 = op0 + T::kOp, pb = smem_u32(smem + S::off_p);
+        const uint32_t LO8 = 8 * T::kPlane, LOP = T::kPP * T::kPlane;
+        uint32_t u = 0, oc = 0, ln = 0;
+        for (int line = blockIdx.x; line < total_lines; line += gridDim.x, ++ln) {
+            // ---- phase A: S = Q K^T   (Q in op0, K in op1)
+            mbar_wait(&bars[B_OP_FULL + 0], (u >> 1) & 1);
+            mbar_wait(&bars[B_OP_FULL + 1], (u >> 1) & 1);
+            mbar_wait(&bars[B_S_EMPTY], (ln & 1) ^ 1);
+            tc_fence_after();
+            for (int ks = 0; ks < KQ; ++ks) {
+                const uint32_t ao = ks * 2 * T::kPlane;
+                mma_split3(tmem, smem_desc(op0 + ao, T::kPlane, 128), smem_desc(op0 + LO8 + ao, T::kPlane, 128),
+                           smem_desc(op1 + ao, T::kPlane, 128), smem_desc(op1 + LO8 + ao, T::kPlane, 128), id_kk_s, ks > 0);
+            }
+            commit_to(&bars[B_S_FULL]);
+            commit_to(&bars[B_OP_EMPTY + 0]);
+            commit_to(&bars[B_OP_EMPTY + 1]);
+            u += 2;
+            mbar_wait(&bars[B_P_FULL], ln & 1);
+            // ---- phase B: per chunk  dP += dO V^T  and  dV = P^T dO      (V in op0, dO in op1)
+            for (int n = 0; n < NCH; ++n, u += 2, ++oc) {
+                mbar_wait(&bars[B_OP_FULL + 0], (u >> 1) & 1);
+                mbar_wait(&bars[B_OP_FULL + 1], (u >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int ks = 0; ks < kNC / 16; ++ks) {
+                    const uint32_t ao = ks * 2 * T::kPlane;
+                    mma_split3(tmem, smem_desc(op1 + ao, T::kPlane, 128), smem_desc(op1 + LO8 + ao, T::kPlane, 128),
+                               smem_desc(op0 + ao, T::kPlane, 128), smem_desc(op0 + LO8 + ao, T::kPlane, 128),
+                               id_kk_s, n > 0 || ks > 0);
+                }
+                mbar_wait(&bars[B_O_EMPTY + (oc & 1)], ((oc >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem + 128 + (oc & 1) * kNC;
+#pragma unroll
+                for (int ks = 0; ks < LK / 16; ++ks) {
+                    const uint32_t ko = ks * 256;     // 16 query pixels = 16 rows x 16 B inside every plane
+                    mma_split3(d, smem_desc(pb + ko, 128, T::kPlane), smem_desc(pb + LOP + ko, 128, T::kPlane),
+                               smem_desc(op1 + ko, 128, T::kPlane), smem_desc(op1 + LO8 + ko, 128, T::kPlane),
+                               id_mn_mn, ks > 0);
+                }
+                commit_to(&bars[B_O_FULL + (oc & 1)]);
+                commit_to(&bars[B_OP_EMPTY + 0]);
+                commit_to(&bars[B_OP_EMPTY + 1]);
+            }
+            commit_to(&bars[B_DP_FULL]);
+            // ---- phase D: dQ = dS K,  dK = dS^T Q      (Q in op0, K in op1, dS in the P planes)
+            mbar_wait(&bars[B_DS_FULL], ln & 1);
+            mbar_wait(&bars[B_OP_FULL + 0], (u >> 1) & 1);
+            mbar_wait(&bars[B_OP_FULL + 1], (u >> 1) & 1);
+            mbar_wait(&bars[B_O_EMPTY + (oc & 1)], ((oc >> 1) & 1) ^ 1);
+            tc_fence_after();
+            {
+                const uint32_t d = tmem + 128 + (oc & 1) * kNC;
+#pragma unroll
+                for (int ks = 0; ks < LK / 16; ++ks) {
+                    const uint32_t ao = ks * 2 * T::kPlane, ko = ks * 256;
+                    mma_split3(d, smem_desc(pb + ao, T::kPlane, 128), smem_desc(pb + LOP + ao, T::kPlane, 128),
+                               smem_desc(op1 + ko, 128, T::kPlane), smem_desc(op1 + LO8 + ko, 128, T::kPlane),
+                               id_k_mn, ks > 0);
+                }
+                commit_to(&bars[B_O_FULL + (oc & 1)]);
+                ++oc;
+            }
+            mbar_wait(&bars[B_O_EMPTY + (oc & 1)], ((oc >> 1) & 1) ^ 1);
+            tc_fence_after();
+            {
+                const uint32_t d = tmem + 128 + (oc & 1) * kNC;
+#pragma unroll
+                for (int ks = 0; ks < LK / 16; ++ks) {
+                    const uint32_t ko = ks * 256;
+                    mma_split3(d, smem_desc(pb + ko, 128, T::kPlane), smem_desc(pb + LOP + ko, 128, T::kPlane),
+                               smem_desc(op0 + ko, 128, T::kPlane), smem_desc(op0 + LO8 + ko, 128, T::kPlane),
+                               id_mn_mn, ks > 0);
+                }
+                commit_to(&bars[B_O_FULL + (oc & 1)]);
+                ++oc;
+            }
+            commit_to(&bars[B_OP_EMPTY + 0]);
+            commit_to(&bars[B_OP_EMPTY + 1]);
+            commit_to(&bars[B_P_EMPTY]);
+            u += 2;
+        }
+    } else if (warp >= 4) {
+        // =============================== converters (256 threads) ===============================
+        const int t = tid - 128;
+        uint32_t g = 0;
+        for (int line = blockIdx.x; line < total_lines; line += gridDim.x) {
+            for (int item = 0; item < NI; ++item, ++g) {
+                const int slot = g & 1, ob = g & 1;
+                mbar_wait(&bars[B_LD_FULL + slot], (g >> 1) & 1);
+                mbar_wait(&bars[B_OP_EMPTY + ob], ((g >> 1) & 1) ^ 1);
+                convert_slot<LK>(smem + S::off_ld + slot * T::kSlot, smem + S::off_op + ob * T::kOp, t);
+                fence_proxy_async();
+                mbar_arrive(&bars[B_OP_FULL + ob]);
+                mbar_arrive(&bars[B_LD_EMPTY + slot]);
+            }
+        }
+    } else {
+        // =============================== P / dS + epilogues (128 threads, TMEM lane == pixel) ===============================
+        const int r = tid;
+        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+        const bool elected = tid == 0;
+        uint32_t oc = 0, ln = 0;
+        // output item i of a line: i < NCH -> dV chunk i; NCH -> dQ; NCH+1 -> dK
+        auto out_map = [&](int i) -> const CUtensorMap * { return i < NCH ? &mdv : (i == NCH ? &mdq : &mdk); };
+        auto out_c0 = [&](int i) { return i < NCH ? i * kNC : 0; };
+        if (!p.col && elected) {                             // prefetch the partial of the very first output item
+            int cw, ch, cb;
+            line_coords(blockIdx.x, cw, ch, cb);
+            uint8_t *dst = smem + S::off_out;
+            mbar_expect_tx(&bars[B_OUT_FULL + 0], T::kSlot);
+            tma_load_4d(dst, out_map(0), &bars[B_OUT_FULL + 0], 0, cw, ch, cb);
+            tma_load_4d(dst + T::kTile, out_map(0), &bars[B_OUT_FULL + 0], 32, cw, ch, cb);
+        }
+        for (int line = blockIdx.x; line < total_lines; line += gridDim.x, ++ln) {
+            int cw, ch, cb;
+            line_coords(line, cw, ch, cb);
+            const bool rvalid = r < p.L;
+            float lse2 = 0.f, dl = 0.f;
+            if (rvalid) {
+                const long pix = p.col ? ((long)cb * p.H + r) * p.W + cw : ((long)cb * p.H + ch) * p.W + r;
+                lse2 = p.lse[pix] * kLog2e;
+                dl = p.delta[pix];
+            }
+            uint8_t *ph = smem + S::off_p + r * 16, *pl = ph + T::kPP * T::kPlane;
+
+            // one output item: TMEM accumulator -> (+ partial) -> swizzled staging -> TMA store
+            auto epilogue_item = [&](int i) {
+                const int os = oc & 1;
+                uint8_t *slot = smem + S::off_out + os * T::kSlot;
+                if (elected) {
+                    if (p.col) {
+                        tma_store_wait_read<1>();
+                        mbar_arrive(&bars[B_OUT_FULL + os]);
+                    } else {
+                        tma_store_wait_read<0>();
+                        int nline = line, ni = i + 1;
+                        if (ni == NO) { ni = 0; nline = line + gridDim.x; }
+                        if (nline < total_lines) {
+                            int w2, h2, b2;
+                            line_coords(nline, w2, h2, b2);
+                            uint8_t *dst = smem + S::off_out + (os ^ 1) * T::kSlot;
+                            mbar_expect_tx(&bars[B_OUT_FULL + (os ^ 1)], T::kSlot);
+                            tma_load_4d(dst, out_map(ni), &bars[B_OUT_FULL + (os ^ 1)], out_c0(ni), w2, h2, b2);
+                            tma_load_4d(dst + T::kTile, out_map(ni), &bars[B_OUT_FULL + (os ^ 1)], out_c0(ni) + 32, w2, h2, b2);
+                        }
+                    }
+                }
+                mbar_wait(&bars[B_OUT_FULL + os], (oc >> 1) & 1);
+                mbar_wait(&bars[B_O_FULL + os], (oc >> 1) & 1);
+                tc_fence_after();
+                float o[kNC];
+#pragma unroll
+                for (int c0 = 0; c0 < kNC; c0 += 16) tmem_ld16(tl + 128 + os * kNC + c0, reinterpret_cast<uint32_t *>(o + c0));
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&bars[B_O_EMPTY + os]);
+                if (r < LK) {
+                    uint8_t *row = slot + r * 128;
+                    const int sw = r & 7;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float4 *dst = reinterpret_cast<float4 *>(row + (j >> 3) * T::kTile + (((j & 7) ^ sw) * 16));
+                        float4 v = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                        if (!p.col) { const float4 q = *dst; v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
+                        *dst = v;
+                    }
+                }
+                fence_proxy_async();
+                named_bar_sync(1, 128);
+                if (elected) {
+                    tma_store_4d(out_map(i), slot, out_c0(i), cw, ch, cb);
+                    tma_store_4d(out_map(i), slot + T::kTile, out_c0(i) + 32, cw, ch, cb);
+                    tma_store_commit();
+                }
+                ++oc;
+            };
+
+            // ---------------- P = exp(S - lse)
+            mbar_wait(&bars[B_S_FULL], ln & 1);
+            tc_fence_after();
+            {
+                float s[LK];
+#pragma unroll
+                for (int c0 = 0; c0 < LK; c0 += 16) tmem_ld16(tl + c0, reinterpret_cast<uint32_t *>(s + c0));
+                tmem_ld_wait();
+                tc_fence_before();
+#pragma unroll
+                for (int j = 0; j < LK; ++j) {
+                    const bool ok = rvalid && j < p.L && !(p.col && j == r);
+                    s[j] = ok ? exp2f(s[j] * kLog2e - lse2) : 0.f;
+                }
+                mbar_wait(&bars[B_P_EMPTY], (ln & 1) ^ 1);
+                if (r < LK) {
+#pragma unroll
+                    for (int kc = 0; kc < T::kPP; ++kc) {
+                        uint4 hi, lo;
+                        split8(s + kc * 8, hi, lo);
+                        *reinterpret_cast<uint4 *>(ph + kc * T::kPlane) = hi;
+                        *reinterpret_cast<uint4 *>(pl + kc * T::kPlane) = lo;
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(&bars[B_P_FULL]);
+            }
+            // ---------------- dV chunks
+            for (int n = 0; n < NCH; ++n) epilogue_item(n);
+            // ---------------- dS = P * (dP - delta)   (all MMAs that read P have completed: DP_FULL is committed after them)
+            mbar_wait(&bars[B_DP_FULL], ln & 1);
+            tc_fence_after();
+            {
+                float dp[LK];
+#pragma unroll
+                for (int c0 = 0; c0 < LK; c0 += 16) tmem_ld16(tl + c0, reinterpret_cast<uint32_t *>(dp + c0));
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&bars[B_S_EMPTY]);
+                if (r < LK) {
+#pragma unroll
+                    for (int kc = 0; kc < T::kPP; ++kc) {
+                        const uint4 hi = *reinterpret_cast<const uint4 *>(ph + kc * T::kPlane);
+                        const uint4 lo = *reinterpret_cast<const uint4 *>(pl + kc * T::kPlane);
+                        const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
+                        float ds[8];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float p0 = bf_lo(hw[e]) + bf_lo(lw[e]), p1 = bf_hi(hw[e]) + bf_hi(lw[e]);
+                            ds[2 * e] = p0 * (dp[kc * 8 + 2 * e] - dl);
+                            ds[2 * e + 1] = p1 * (dp[kc * 8 + 2 * e + 1] - dl);
+                        }
+                        uint4 dh, dlo;
+                        split8(ds, dh, dlo);
+                        *reinterpret_cast<uint4 *>(ph + kc * T::kPlane) = dh;
+                        *reinterpret_cast<uint4 *>(pl + kc * T::kPlane) = dlo;
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(&bars[B_DS_FULL]);
+            }
+            // ---------------- dQ, dK
+            epilogue_item(NCH);
+            epilogue_item(NCH + 1);
+        }
+        if (elected) tma_store_wait_all<0>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<kTmemCols>(tmem);
+}
+
+// delta[pix] = sum_c dout[pix][c] * out[pix][c]   (channels-last: one warp per pixel, float4 lanes)
+__global__ void __launch_bounds__(256) cca_delta_nhwc_kernel(const float4 *__restrict__ dout, const float4 *__restrict__ out,
+                                                             float *__restrict__ delta, long npix, int c4)
+{
+    const long pix = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (pix >= npix) return;
+    const int lane = threadIdx.x & 31;
+    const float4 *a = dout + pix * c4, *b = out + pix * c4;
+    float s = 0.f;
+    for (int i = lane; i < c4; i += 32) {
+        const float4 x = __ldg(a + i), y = __ldg(b + i);
+        s += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) delta[pix] = s;
+}
+
+template <int LK>
+cudaError_t launch_bwd_pass(const void *dout, const void *q, const void *k, const void *v, const float *lse, const float *delta,
+                            void *dq, void *dk, void *dv, Dims d, bool col, cudaStream_t st, const char **why)
+{
+    CUtensorMap mq, mk, mv, mdo, mdq, mdk, mdv;
+    const bool ok = make_map(&mq, q, d.B, d.H, d.W, d.Cq, LK, col) && make_map(&mk, k, d.B, d.H, d.W, d.Cq, LK, col) &&
+                    make_map(&mv, v, d.B, d.H, d.W, d.C, LK, col) && make_map(&mdo, dout, d.B, d.H, d.W, d.C, LK, col) &&
+                    make_map(&mdq, dq, d.B, d.H, d.W, d.Cq, LK, col) && make_map(&mdk, dk, d.B, d.H, d.W, d.Cq, LK, col) &&
+                    make_map(&mdv, dv, d.B, d.H, d.W, d.C, LK, col);
+    if (!ok) {
+        if (why) *why = "cuTensorMapEncodeTiled failed";
+        return cudaErrorInvalidValue;
+    }
+    BwdParams p;
+    p.B = d.B; p.H = d.H; p.W = d.W; p.C = d.C; p.Cq = d.Cq;
+    p.L = col ? d.H : d.W; p.NL = col ? d.W : d.H; p.col = col ? 1 : 0;
+    p.lse = lse; p.delta = delta;
+    auto kern = cca_tc_bwd_kernel<LK>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<LK>::kBytes);
+    if (e != cudaSuccess) return e;
+    const int lines = d.B * p.NL;
+    const int grid = lines < sm_count() ? lines : sm_count();
+    kern<<<grid, kThreads, BwdSmem<LK>::kBytes, st>>>(mq, mk, mv, mdo, mdq, mdk, mdv, p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool tc_backward_supported(Dims d, int dtype) { return tc::shape_supported(d, dtype); }
+
+// all tensors channels-last (NHWC) fp32; ws = delta [B,H,W]
+cudaError_t tc_backward(const void *dout, const void *q, const void *k, const void *v, const void *out, const float *lse,
+                        void *dq, void *dk, void *dv, void *ws, Dims d, int dtype, cudaStream_t st, const char **why)
+{
+    (void)dtype;
+    float *delta = reinterpret_cast<float *>(ws);
+    const long npix = (long)d.B * d.H * d.W;
+    cca_delta_nhwc_kernel<<<(unsigned)((npix + 7) / 8), 256, 0, st>>>(reinterpret_cast<const float4 *>(dout),
+                                                                     reinterpret_cast<const float4 *>(out), delta, npix, d.C / 4);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    e = lk_for(d.H) == 80 ? launch_bwd_pass<80>(dout, q, k, v, lse, delta, dq, dk, dv, d, true, st, why)
+                          : launch_bwd_pass<112>(dout, q, k, v, lse, delta, dq, dk, dv, d, true, st, why);
+    if (e != cudaSuccess) return e;
+    e = lk_for(d.W) == 80 ? launch_bwd_pass<80>(dout, q, k, v, lse, delta, dq, dk, dv, d, false, st, why)
+                          : launch_bwd_pass<112>(dout, q, k, v, lse, delta, dq, dk, dv, d, false, st, why);
+    return e;
+}
+
+}  // namespace cca

@@ -1,0 +1,158 @@
+// Pieces shared by the tcgen05 forward and backward kernels (channels-last, fp32 I/O, bf16x3 split).
+#pragma once
+#include <mutex>
+
+#include "cca_common.cuh"
+#include "cca_sm100.cuh"
+
+namespace cca {
+namespace tc {
+using namespace sm100;
+
+constexpr int kNC = 64;   // channels per chunk (one ring slot = [LK px][64 ch] fp32 = two swizzled TMA tiles)
+
+// Thread layout of both kernels:
+//   warps 0-3   (128 thr) : TMEM group -- softmax / dS and the epilogues (TMEM lane == pixel)
+//   warps 4-11  (256 thr) : converters -- fp32 staging tile -> bf16 hi/lo operand planes
+//   warp 12               : TMA producer (one elected lane)
+//   warp 13               : MMA issuer (whole warp converged, tcgen05.mma under elect.sync)
+constexpr int kThreads = 448;
+constexpr int kConvThreads = 256;
+constexpr int kWarpProducer = 12, kWarpMma = 13;
+
+template <int LK> struct Tiles {
+    static constexpr int kTile = LK * 128;             // [LK px][32 fp32], SWIZZLE_128B
+    static constexpr int kSlot = 2 * kTile;            // 64 channels
+    static constexpr int kPlane = LK * 16;             // operand plane: LK rows x 16 B (8 bf16)
+    static constexpr int kOp = 2 * 8 * kPlane;         // hi + lo, 8 planes = 64 channels
+    static constexpr int kPP = LK / 8;                 // planes of a [LK x LK] pixel-pixel matrix (P, dS)
+    static constexpr int kP = 2 * kPP * kPlane;        // hi + lo
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b)
+{
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // low half = a, high half = b
+    return r;
+}
+// (a, b) -> packed bf16 hi pair and lo pair, x = hi + lo up to ~2^-17 |x|
+__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo)
+{
+    hi = pack_bf16(a, b);
+    const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xFFFF0000u);
+    lo = pack_bf16(a - ah, b - bh);
+}
+__device__ __forceinline__ void split8(const float *v, uint4 &hi, uint4 &lo)
+{
+    split2(v[0], v[1], hi.x, lo.x); split2(v[2], v[3], hi.y, lo.y);
+    split2(v[4], v[5], hi.z, lo.z); split2(v[6], v[7], hi.w, lo.w);
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, %1;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred) : "r"(0xFFFFFFFFu));
+    return pred != 0;
+}
+
+// Converter: one staged slot ([LK px][64 ch] fp32 as two swizzled tiles) -> hi/lo operand planes
+// [8-channel chunk][pixel][16 B].  256 threads: thread t handles pixel (t & 127), octets 4*(t>>7)..+3.
+template <int LK>
+__device__ __forceinline__ void convert_slot(const uint8_t *slot, uint8_t *op, int t)
+{
+    using T = Tiles<LK>;
+    const int r = t & 127, half = t >> 7;
+    if (r >= LK) return;
+    const uint8_t *src = slot + r * 128 + half * T::kTile;      // octets 0-3 live in tile 0, 4-7 in tile 1
+    uint8_t *dh = op + r * 16 + half * 4 * T::kPlane, *dl = dh + 8 * T::kPlane;
+    const int sw = r & 7;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 a = *reinterpret_cast<const float4 *>(src + (((2 * j) ^ sw) * 16));
+        const float4 b = *reinterpret_cast<const float4 *>(src + (((2 * j + 1) ^ sw) * 16));
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        *reinterpret_cast<uint4 *>(dh + j * T::kPlane) = hi;
+        *reinterpret_cast<uint4 *>(dl + j * T::kPlane) = lo;
+    }
+}
+
+// D (+)= A*B with the bf16x3 split: Ah*Bh + Ah*Bl + Al*Bh.  Executed by the whole (converged) MMA warp.
+__device__ __forceinline__ void mma_split3(uint32_t d, uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl,
+                                           uint32_t idesc, bool accumulate)
+{
+    if (elect_one()) {
+        mma_f16(d, ah, bh, idesc, accumulate);
+        mma_f16(d, ah, bl, idesc, true);
+        mma_f16(d, al, bh, idesc, true);
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void commit_to(uint64_t *bar)
+{
+    if (elect_one()) mma_commit(bar);
+    __syncwarp();
+}
+
+// ---- host: TMA tensor maps over channels-last fp32 tensors -------------------------------------
+typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                             const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeFn get_encode()
+{
+    static EncodeFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        cudaDriverEntryPointQueryResult qr;
+        void *p = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeFn>(p);
+    });
+    return fn;
+}
+// NHWC fp32 tensor [B,H,W,C]; box = [32 ch] x [LK pixels along W (row pass) or along H (column pass)]
+inline bool make_map(CUtensorMap *m, const void *base, int B, int H, int W, int C, int LK, bool col)
+{
+    EncodeFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    cuuint32_t box[4] = {32, col ? 1u : (cuuint32_t)LK, col ? (cuuint32_t)LK : 1u, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(base), dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+inline int lk_for(int L) { return L <= 80 ? 80 : (L <= 112 ? 112 : 0); }
+inline int sm_count()
+{
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return n;
+}
+inline bool shape_supported(Dims d, int dtype)
+{
+    if (dtype != CCA_F32) return false;
+    if (d.Cq % 16 != 0 || d.Cq > 64 || d.Cq < 16 || d.C % kNC != 0) return false;
+    if (lk_for(d.H) == 0 || lk_for(d.W) == 0) return false;
+    return get_encode() != nullptr;
+}
+
+}  // namespace tc
+}  // namespace cca

@@ -9,29 +9,23 @@
 // One persistent CTA per SM walks over lines.  Per line (L <= LK pixels, padded to LK):
 //   TMA producer (1 thread)   : 4-D tiled loads [LK px][32 ch] fp32, SWIZZLE_128B, OOB pixels zero-filled,
 //                               into a 2-slot ring: Q, K, then the V chunks (64 channels each).
-//   converter warps (128 thr) : fp32 -> bf16 hi + bf16 lo split (x = hi + lo to ~2^-17), written as UMMA
+//   converter warps (256 thr) : fp32 -> bf16 hi + bf16 lo split (x = hi + lo to ~2^-17), written as UMMA
 //                               canonical no-swizzle operand planes [8-channel chunk][pixel][16 B].
-//   MMA issuer (1 thread)     : S = Q K^T as 3 bf16 MMAs per k-step (hi*hi + hi*lo + lo*hi, fp32 accumulate
+//   MMA warp (elect.sync)     : S = Q K^T as 3 bf16 MMAs per k-step (hi*hi + hi*lo + lo*hi, fp32 accumulate
 //                               in TMEM, M=128 N=LK K=16), then per V chunk O = P V (M=128 N=64, K = pixels).
 //   softmax/epilogue (128 thr): TMEM -> registers (one query pixel per thread), exp2-based softmax, P split
 //                               hi/lo into K-major operand planes; per V chunk TMEM -> scale/merge ->
 //                               swizzled smem tile -> TMA store.
 // All inter-role hand-offs are mbarriers (TMA complete_tx, tcgen05.commit, thread arrives).
-#include <mutex>
-#include <unordered_map>
-
-#include "cca_common.cuh"
-#include "cca_sm100.cuh"
+#include "cca_tc_common.cuh"
 
 namespace cca {
 namespace {
-using namespace sm100;
+using namespace tc;
 
-constexpr int kTcThreads = 320;     // warps 0-3 softmax/epilogue, 4-7 convert, 8 TMA producer, 9 MMA issuer
-constexpr int kNC = 64;             // channels per V chunk
 constexpr int kTmemCols = 256;      // S: [0,128)  O0: [128,192)  O1: [192,256)
 
-struct TcParams {
+struct FwdParams {
     int B, H, W, C, Cq;
     int L;        // pixels per line (H for the column pass, W for the row pass)
     int NL;       // lines per sample
@@ -41,54 +35,32 @@ struct TcParams {
     long long *dbg;   // optional timeline buffer (4 roles x 512 stamps), CTA 0 only; nullptr in production
 };
 
-#define CCA_STAMP(role)                                                        \
-    do {                                                                       \
-        if (p.dbg && blockIdx.x == 0 && dbg_n < 512) p.dbg[(role) * 512 + dbg_n++] = clock64(); \
+#define CCA_STAMP(role)                                                                          \
+    do {                                                                                         \
+        if (p.dbg && blockIdx.x == 0 && dbg_n < 512) p.dbg[(role) * 512 + dbg_n++] = clock64();  \
     } while (0)
 
-template <int LK> struct Smem {
-    static constexpr int kTile = LK * 128;             // [LK px][32 fp32] swizzled TMA tile
-    static constexpr int kSlot = 2 * kTile;            // 64 channels
-    static constexpr int kPlane = LK * 16;             // one operand plane: LK rows x 16 B
-    static constexpr int kOp = 2 * 8 * kPlane;         // hi + lo, 8 planes (64 contraction / output channels)
-    static constexpr int kP = 2 * (LK / 8) * kPlane;   // P hi + lo, LK/8 planes of LK rows
-    static constexpr int off_ld = 0;                   // 2 load slots
-    static constexpr int off_out = off_ld + 2 * kSlot; // 2 out slots
-    static constexpr int off_op = off_out + 2 * kSlot; // 2 operand buffers
-    static constexpr int off_p = off_op + 2 * kOp;
-    static constexpr int off_tail = off_p + kP;        // 256 B pad: M=128 MMAs read 16 rows past LK rows
+template <int LK> struct FwdSmem {
+    using T = Tiles<LK>;
+    static constexpr int off_ld = 0;                      // 2 load slots
+    static constexpr int off_out = off_ld + 2 * T::kSlot; // 2 out slots
+    static constexpr int off_op = off_out + 2 * T::kSlot; // 2 operand buffers
+    static constexpr int off_p = off_op + 2 * T::kOp;
+    static constexpr int off_tail = off_p + T::kP;        // 256 B pad: M=128 MMAs read 16 rows past LK rows
     static constexpr int off_bar = off_tail + 256;
-    static constexpr int kBytes = off_bar + 256 + 1024; // + alignment slack
+    static constexpr int kBytes = off_bar + 256 + 1024;   // + alignment slack
 };
 
 enum { B_LD_FULL = 0, B_LD_EMPTY = 2, B_OP_FULL = 4, B_OP_EMPTY = 6, B_S_FULL = 8, B_S_EMPTY = 9, B_P_FULL = 10,
        B_P_EMPTY = 11, B_O_FULL = 12, B_O_EMPTY = 14, B_OUT_FULL = 16, B_COUNT = 18 };
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b)
-{
-    uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // low half = a, high half = b
-    return r;
-}
-// x -> (hi, lo) with hi = bf16(x), lo = bf16(x - hi); packs two values
-__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo)
-{
-    hi = pack_bf16(a, b);
-    const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xFFFF0000u);
-    lo = pack_bf16(a - ah, b - bh);
-}
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
-{
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
 template <int LK>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
-                  const __grid_constant__ CUtensorMap mv, const __grid_constant__ CUtensorMap mo, TcParams p)
+                  const __grid_constant__ CUtensorMap mv, const __grid_constant__ CUtensorMap mo, FwdParams p)
 {
-    using S = Smem<LK>;
+    using T = Tiles<LK>;
+    using S = FwdSmem<LK>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S::off_bar);
@@ -100,9 +72,9 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&bars[B_LD_FULL + i], 1);   mbar_init(&bars[B_LD_EMPTY + i], 128);
-            mbar_init(&bars[B_OP_FULL + i], 128); mbar_init(&bars[B_OP_EMPTY + i], 1);
-            mbar_init(&bars[B_O_FULL + i], 1);    mbar_init(&bars[B_O_EMPTY + i], 128);
+            mbar_init(&bars[B_LD_FULL + i], 1);            mbar_init(&bars[B_LD_EMPTY + i], kConvThreads);
+            mbar_init(&bars[B_OP_FULL + i], kConvThreads); mbar_init(&bars[B_OP_EMPTY + i], 1);
+            mbar_init(&bars[B_O_FULL + i], 1);             mbar_init(&bars[B_O_EMPTY + i], 128);
             mbar_init(&bars[B_OUT_FULL + i], 1);
         }
         mbar_init(&bars[B_S_FULL], 1); mbar_init(&bars[B_S_EMPTY], 128);
@@ -123,7 +95,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
         if (p.col) { cw = i; ch = 0; } else { cw = 0; ch = i; }
     };
 
-    if (warp == 8) {
+    if (warp == kWarpProducer) {
         // =============================== TMA producer ===============================
         if (lane == 0) {
             uint32_t g = 0;
@@ -135,75 +107,69 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                     const int slot = g & 1;
                     mbar_wait(&bars[B_LD_EMPTY + slot], ((g >> 1) & 1) ^ 1);
                     CCA_STAMP(0);
-                    uint8_t *dst = smem + S::off_ld + slot * S::kSlot;
-                    mbar_expect_tx(&bars[B_LD_FULL + slot], S::kSlot);
+                    uint8_t *dst = smem + S::off_ld + slot * T::kSlot;
+                    mbar_expect_tx(&bars[B_LD_FULL + slot], T::kSlot);
                     const CUtensorMap *m = item == 0 ? &mq : (item == 1 ? &mk : &mv);
                     const int c0 = item < 2 ? 0 : (item - 2) * kNC;
                     tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, cb);
-                    tma_load_4d(dst + S::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, cb);
+                    tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, cb);
                 }
             }
         }
-    } else if (warp == 9) {
-        // =============================== MMA issuer ===============================
-        if (lane == 0) {
-            const uint32_t idesc_s = instr_desc(kFmtBF16, kFmtBF16, 128, LK, false, false);
-            const uint32_t idesc_o = instr_desc(kFmtBF16, kFmtBF16, 128, kNC, false, true);
-            const uint32_t op_base = smem_u32(smem + S::off_op), p_base = smem_u32(smem + S::off_p);
-            uint32_t u = 0, oc = 0, ln = 0;
-            int dbg_n = 0;
-            for (int line = blockIdx.x; line < total_lines; line += gridDim.x, ++ln) {
-                // ---- S = Q K^T  (Q in operand buffer u&1, K in (u+1)&1)
-                const uint32_t qb = op_base + (u & 1) * S::kOp, kb = op_base + ((u + 1) & 1) * S::kOp;
+    } else if (warp == kWarpMma) {
+        // =============================== MMA issuer (whole warp, elect.sync inside) ===============================
+        const uint32_t idesc_s = instr_desc(kFmtBF16, kFmtBF16, 128, LK, false, false);
+        const uint32_t idesc_o = instr_desc(kFmtBF16, kFmtBF16, 128, kNC, false, true);
+        const uint32_t op_base = smem_u32(smem + S::off_op), p_base = smem_u32(smem + S::off_p);
+        uint32_t u = 0, oc = 0, ln = 0;
+        int dbg_n = lane == 0 ? 0 : 512;
+        for (int line = blockIdx.x; line < total_lines; line += gridDim.x, ++ln) {
+            // ---- S = Q K^T  (Q in operand buffer u&1, K in (u+1)&1)
+            const uint32_t qb = op_base + (u & 1) * T::kOp, kb = op_base + ((u + 1) & 1) * T::kOp;
+            mbar_wait(&bars[B_OP_FULL + (u & 1)], (u >> 1) & 1);
+            mbar_wait(&bars[B_OP_FULL + ((u + 1) & 1)], ((u + 1) >> 1) & 1);
+            mbar_wait(&bars[B_S_EMPTY], (ln & 1) ^ 1);
+            tc_fence_after();
+            CCA_STAMP(2);
+            for (int ks = 0; ks < KQ; ++ks) {
+                const uint32_t ao = ks * 2 * T::kPlane;
+                mma_split3(tmem, smem_desc(qb + ao, T::kPlane, 128), smem_desc(qb + 8 * T::kPlane + ao, T::kPlane, 128),
+                           smem_desc(kb + ao, T::kPlane, 128), smem_desc(kb + 8 * T::kPlane + ao, T::kPlane, 128),
+                           idesc_s, ks > 0);
+            }
+            commit_to(&bars[B_S_FULL]);
+            commit_to(&bars[B_OP_EMPTY + (u & 1)]);
+            commit_to(&bars[B_OP_EMPTY + ((u + 1) & 1)]);
+            u += 2;
+            // ---- O chunks = P V
+            CCA_STAMP(2);
+            mbar_wait(&bars[B_P_FULL], ln & 1);
+            CCA_STAMP(2);
+            for (int n = 0; n < NCH; ++n, ++u, ++oc) {
+                const uint32_t vb = op_base + (u & 1) * T::kOp;
                 mbar_wait(&bars[B_OP_FULL + (u & 1)], (u >> 1) & 1);
-                mbar_wait(&bars[B_OP_FULL + ((u + 1) & 1)], ((u + 1) >> 1) & 1);
-                mbar_wait(&bars[B_S_EMPTY], (ln & 1) ^ 1);
+                mbar_wait(&bars[B_O_EMPTY + (oc & 1)], ((oc >> 1) & 1) ^ 1);
                 tc_fence_after();
                 CCA_STAMP(2);
-                for (int ks = 0; ks < KQ; ++ks) {
-                    const uint32_t ao = ks * 2 * S::kPlane;
-                    const uint64_t qh = smem_desc(qb + ao, S::kPlane, 128), ql = smem_desc(qb + 8 * S::kPlane + ao, S::kPlane, 128);
-                    const uint64_t kh = smem_desc(kb + ao, S::kPlane, 128), kl = smem_desc(kb + 8 * S::kPlane + ao, S::kPlane, 128);
-                    mma_f16(tmem, qh, kh, idesc_s, ks > 0);
-                    mma_f16(tmem, qh, kl, idesc_s, true);
-                    mma_f16(tmem, ql, kh, idesc_s, true);
+                const uint32_t d = tmem + 128 + (oc & 1) * kNC;
+#pragma unroll
+                for (int ks = 0; ks < LK / 16; ++ks) {
+                    const uint32_t ao = ks * 2 * T::kPlane, bo = ks * 256;
+                    mma_split3(d, smem_desc(p_base + ao, T::kPlane, 128), smem_desc(p_base + T::kPP * T::kPlane + ao, T::kPlane, 128),
+                               smem_desc(vb + bo, 128, T::kPlane), smem_desc(vb + 8 * T::kPlane + bo, 128, T::kPlane),
+                               idesc_o, ks > 0);
                 }
-                mma_commit(&bars[B_S_FULL]);
-                mma_commit(&bars[B_OP_EMPTY + (u & 1)]);
-                mma_commit(&bars[B_OP_EMPTY + ((u + 1) & 1)]);
-                u += 2;
-                // ---- O chunks = P V
+                commit_to(&bars[B_O_FULL + (oc & 1)]);
+                commit_to(&bars[B_OP_EMPTY + (u & 1)]);
                 CCA_STAMP(2);
-                mbar_wait(&bars[B_P_FULL], ln & 1);
-                CCA_STAMP(2);
-                for (int n = 0; n < NCH; ++n, ++u, ++oc) {
-                    const uint32_t vb = op_base + (u & 1) * S::kOp;
-                    mbar_wait(&bars[B_OP_FULL + (u & 1)], (u >> 1) & 1);
-                    mbar_wait(&bars[B_O_EMPTY + (oc & 1)], ((oc >> 1) & 1) ^ 1);
-                    tc_fence_after();
-                    CCA_STAMP(2);
-                    const uint32_t d = tmem + 128 + (oc & 1) * kNC;
-                    for (int ks = 0; ks < LK / 16; ++ks) {
-                        const uint32_t ao = ks * 2 * S::kPlane, bo = ks * 256;
-                        const uint64_t ph = smem_desc(p_base + ao, S::kPlane, 128);
-                        const uint64_t pl = smem_desc(p_base + (LK / 8) * S::kPlane + ao, S::kPlane, 128);
-                        const uint64_t vh = smem_desc(vb + bo, 128, S::kPlane), vl = smem_desc(vb + 8 * S::kPlane + bo, 128, S::kPlane);
-                        mma_f16(d, ph, vh, idesc_o, ks > 0);
-                        mma_f16(d, ph, vl, idesc_o, true);
-                        mma_f16(d, pl, vh, idesc_o, true);
-                    }
-                    mma_commit(&bars[B_O_FULL + (oc & 1)]);
-                    mma_commit(&bars[B_OP_EMPTY + (u & 1)]);
-                    CCA_STAMP(2);
-                }
-                mma_commit(&bars[B_P_EMPTY]);
             }
+            commit_to(&bars[B_P_EMPTY]);
         }
     } else if (warp >= 4) {
-        // =============================== converters (128 threads) ===============================
-        const int r = tid - 128;                     // pixel row handled by this thread
+        // =============================== converters (256 threads) ===============================
+        const int t = tid - 128;
         uint32_t g = 0;
-        int dbg_n = r == 0 ? 0 : 512;
+        int dbg_n = t == 0 ? 0 : 512;
         for (int line = blockIdx.x; line < total_lines; line += gridDim.x) {
             for (int item = 0; item < 2 + NCH; ++item, ++g) {
                 const int slot = g & 1, ob = g & 1;
@@ -211,23 +177,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                 CCA_STAMP(1);
                 mbar_wait(&bars[B_OP_EMPTY + ob], ((g >> 1) & 1) ^ 1);
                 CCA_STAMP(1);
-                if (r < LK) {
-                    const uint8_t *src = smem + S::off_ld + slot * S::kSlot + r * 128;
-                    uint8_t *dh = smem + S::off_op + ob * S::kOp + r * 16, *dl = dh + 8 * S::kPlane;
-                    const int sw = r & 7;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {        // 8 channels = two 16-byte chunks of the swizzled tile row
-                        const uint8_t *t = src + (j >> 2) * S::kTile;
-                        const int c0 = (2 * (j & 3)) ^ sw, c1 = (2 * (j & 3) + 1) ^ sw;
-                        const float4 a = *reinterpret_cast<const float4 *>(t + c0 * 16);
-                        const float4 b = *reinterpret_cast<const float4 *>(t + c1 * 16);
-                        uint4 hi, lo;
-                        split2(a.x, a.y, hi.x, lo.x); split2(a.z, a.w, hi.y, lo.y);
-                        split2(b.x, b.y, hi.z, lo.z); split2(b.z, b.w, hi.w, lo.w);
-                        *reinterpret_cast<uint4 *>(dh + j * S::kPlane) = hi;
-                        *reinterpret_cast<uint4 *>(dl + j * S::kPlane) = lo;
-                    }
-                }
+                convert_slot<LK>(smem + S::off_ld + slot * T::kSlot, smem + S::off_op + ob * T::kOp, t);
                 fence_proxy_async();
                 mbar_arrive(&bars[B_OP_FULL + ob]);
                 mbar_arrive(&bars[B_LD_EMPTY + slot]);
@@ -241,14 +191,13 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
         const bool elected = tid == 0;
         uint32_t oc = 0, ln = 0;
         int dbg_n = tid == 0 ? 0 : 512;
-        const bool have_lines = (int)blockIdx.x < total_lines;
-        if (!p.col && elected && have_lines) {               // prefetch the partial of the very first chunk
+        if (!p.col && elected) {                             // prefetch the partial of the very first chunk
             int cw, ch, cb;
             line_coords(blockIdx.x, cw, ch, cb);
             uint8_t *dst = smem + S::off_out;
-            mbar_expect_tx(&bars[B_OUT_FULL + 0], S::kSlot);
+            mbar_expect_tx(&bars[B_OUT_FULL + 0], T::kSlot);
             tma_load_4d(dst, &mo, &bars[B_OUT_FULL + 0], 0, cw, ch, cb);
-            tma_load_4d(dst + S::kTile, &mo, &bars[B_OUT_FULL + 0], 32, cw, ch, cb);
+            tma_load_4d(dst + T::kTile, &mo, &bars[B_OUT_FULL + 0], 32, cw, ch, cb);
         }
         for (int line = blockIdx.x; line < total_lines; line += gridDim.x, ++ln) {
             int cw, ch, cb;
@@ -293,21 +242,17 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                     p.lse[pix] = mm + logf(lt);
                 }
             }
-            // ---------------- P -> K-major operand planes (hi, lo)
+            // ---------------- P -> operand planes [key chunk][query pixel][16 B] (hi, lo)
             CCA_STAMP(3);
             mbar_wait(&bars[B_P_EMPTY], (ln & 1) ^ 1);
             if (r < LK) {
-                uint8_t *ph = smem + S::off_p + r * 16, *pl = ph + (LK / 8) * S::kPlane;
+                uint8_t *ph = smem + S::off_p + r * 16, *pl = ph + T::kPP * T::kPlane;
 #pragma unroll
-                for (int kc = 0; kc < LK / 8; ++kc) {
-                    uint4 hi, lo;
-                    const float *v = s + kc * 8;
-                    if (rvalid) {
-                        split2(v[0], v[1], hi.x, lo.x); split2(v[2], v[3], hi.y, lo.y);
-                        split2(v[4], v[5], hi.z, lo.z); split2(v[6], v[7], hi.w, lo.w);
-                    } else { hi = make_uint4(0, 0, 0, 0); lo = hi; }
-                    *reinterpret_cast<uint4 *>(ph + kc * S::kPlane) = hi;
-                    *reinterpret_cast<uint4 *>(pl + kc * S::kPlane) = lo;
+                for (int kc = 0; kc < T::kPP; ++kc) {
+                    uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+                    if (rvalid) split8(s + kc * 8, hi, lo);
+                    *reinterpret_cast<uint4 *>(ph + kc * T::kPlane) = hi;
+                    *reinterpret_cast<uint4 *>(pl + kc * T::kPlane) = lo;
                 }
             }
             fence_proxy_async();
@@ -316,7 +261,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
             // ---------------- epilogue per V chunk
             for (int n = 0; n < NCH; ++n, ++oc) {
                 const int os = oc & 1;
-                uint8_t *slot = smem + S::off_out + os * S::kSlot;
+                uint8_t *slot = smem + S::off_out + os * T::kSlot;
                 if (elected) {
                     if (p.col) {
                         tma_store_wait_read<1>();              // the store that used this slot two chunks ago has drained
@@ -328,10 +273,10 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                         if (nline < total_lines) {
                             int w2, h2, b2;
                             line_coords(nline, w2, h2, b2);
-                            uint8_t *dst = smem + S::off_out + (os ^ 1) * S::kSlot;
-                            mbar_expect_tx(&bars[B_OUT_FULL + (os ^ 1)], S::kSlot);
+                            uint8_t *dst = smem + S::off_out + (os ^ 1) * T::kSlot;
+                            mbar_expect_tx(&bars[B_OUT_FULL + (os ^ 1)], T::kSlot);
                             tma_load_4d(dst, &mo, &bars[B_OUT_FULL + (os ^ 1)], nn * kNC, w2, h2, b2);
-                            tma_load_4d(dst + S::kTile, &mo, &bars[B_OUT_FULL + (os ^ 1)], nn * kNC + 32, w2, h2, b2);
+                            tma_load_4d(dst + T::kTile, &mo, &bars[B_OUT_FULL + (os ^ 1)], nn * kNC + 32, w2, h2, b2);
                         }
                     }
                 }
@@ -352,7 +297,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                     const int sw = r & 7;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {               // 16 chunks of 4 channels
-                        float4 *dst = reinterpret_cast<float4 *>(row + (j >> 3) * S::kTile + (((j & 7) ^ sw) * 16));
+                        float4 *dst = reinterpret_cast<float4 *>(row + (j >> 3) * T::kTile + (((j & 7) ^ sw) * 16));
                         float4 v = make_float4(o[4 * j] * sa, o[4 * j + 1] * sa, o[4 * j + 2] * sa, o[4 * j + 3] * sa);
                         if (!p.col) {
                             const float4 q = *dst;
@@ -365,7 +310,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                 named_bar_sync(1, 128);
                 if (elected) {
                     tma_store_4d(&mo, slot, n * kNC, cw, ch, cb);
-                    tma_store_4d(&mo, slot + S::kTile, n * kNC + 32, cw, ch, cb);
+                    tma_store_4d(&mo, slot + T::kTile, n * kNC + 32, cw, ch, cb);
                     tma_store_commit();
                 }
                 CCA_STAMP(3);
@@ -378,44 +323,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
     if (warp == 0) tmem_dealloc<kTmemCols>(tmem);
 }
 
-// ---------------------------------------------------------------------------------------------
-// host side
-// ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                             const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeFn get_encode()
-{
-    static EncodeFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        cudaDriverEntryPointQueryResult qr;
-        void *p = nullptr;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
-            qr == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeFn>(p);
-    });
-    return fn;
-}
-
-// NHWC fp32 tensor [B,H,W,C]; box = [32 ch] x [LK pixels along W (row pass) or H (column pass)]
-bool make_map(CUtensorMap *m, const void *base, int B, int H, int W, int C, int LK, bool col)
-{
-    EncodeFn enc = get_encode();
-    if (!enc) return false;
-    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-    cuuint32_t box[4] = {32, col ? 1u : (cuuint32_t)LK, col ? (cuuint32_t)LK : 1u, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(base), dims, strides, box, es,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 long long *g_dbg = nullptr;   // set through cca_b200__set_debug_buffer (profiling aid, not part of the ABI)
-
-int lk_for(int L) { return L <= 80 ? 80 : (L <= 112 ? 112 : 0); }
 
 template <int LK>
 cudaError_t launch_pass(const void *q, const void *k, const void *v, void *out, float *lse, float2 *stats, Dims d,
@@ -427,23 +335,17 @@ cudaError_t launch_pass(const void *q, const void *k, const void *v, void *out, 
         if (why) *why = "cuTensorMapEncodeTiled failed";
         return cudaErrorInvalidValue;
     }
-    TcParams p;
+    FwdParams p;
     p.B = d.B; p.H = d.H; p.W = d.W; p.C = d.C; p.Cq = d.Cq;
     p.L = col ? d.H : d.W; p.NL = col ? d.W : d.H; p.col = col ? 1 : 0;
     p.stats = stats; p.lse = lse;
     p.dbg = g_dbg ? g_dbg + (col ? 0 : 2048) : nullptr;
     auto kern = cca_tc_fwd_kernel<LK>;
-    static int sm_count = 0;
-    if (!sm_count) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    }
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<LK>::kBytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem<LK>::kBytes);
     if (e != cudaSuccess) return e;
     const int lines = d.B * p.NL;
-    const int grid = lines < sm_count ? lines : sm_count;
-    kern<<<grid, kTcThreads, Smem<LK>::kBytes, st>>>(mq, mk, mv, mo, p);
+    const int grid = lines < sm_count() ? lines : sm_count();
+    kern<<<grid, kThreads, FwdSmem<LK>::kBytes, st>>>(mq, mk, mv, mo, p);
     count_launch();
     return cudaGetLastError();
 }
@@ -452,13 +354,7 @@ cudaError_t launch_pass(const void *q, const void *k, const void *v, void *out, 
 
 void set_tc_debug_buffer(void *p) { g_dbg = reinterpret_cast<long long *>(p); }
 
-bool tc_forward_supported(Dims d, int dtype)
-{
-    if (dtype != CCA_F32) return false;
-    if (d.Cq % 16 != 0 || d.Cq > 64 || d.Cq < 16 || d.C % kNC != 0) return false;
-    if (lk_for(d.H) == 0 || lk_for(d.W) == 0) return false;
-    return get_encode() != nullptr;
-}
+bool tc_forward_supported(Dims d, int dtype) { return tc::shape_supported(d, dtype); }
 
 // q,k,v,out are channels-last (NHWC) fp32.
 cudaError_t tc_forward(const void *q, const void *k, const void *v, void *out, float *lse, void *ws, Dims d, int dtype,

@@ -76,24 +76,39 @@ def cca_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, impl: str = "
 
 
 def cca_backward(dout, q, k, v, out, lse, impl: str = "auto"):
-    """Gradients (dq, dk, dv) of ``cca_forward`` given dout and the saved forward tensors."""
+    """Gradients (dq, dk, dv) of ``cca_forward`` given dout and the saved forward tensors.
+
+    Same ``impl`` / memory-format rules as ``cca_forward``: the tensor-core kernels take and return
+    channels-last tensors, the generic kernels NCHW-contiguous ones.
+    """
     _check_inputs(q, k, v)
     lib = capi.load()
-    dout, q, k, v, out = (t.contiguous() for t in (dout, q, k, v, out))
     if dout.dtype != q.dtype or out.dtype != q.dtype or dout.shape != v.shape or out.shape != v.shape:
         raise RuntimeError("ccnet_b200: dout/out must match v in shape and dtype")
-    lse = lse.contiguous()
     B, Cq, H, W = q.shape
     C = v.shape[1]
     dt = _DTYPES[q.dtype]
+    flags = _IMPL_FLAGS[impl]
+    use_tc = impl in ("auto", "tc") and lib.cca_b200_tc_supported(B, Cq, C, H, W, dt) == 1
+    if impl == "tc" and not use_tc:
+        raise RuntimeError(f"ccnet_b200: tensor-core kernels do not cover q{tuple(q.shape)} v{tuple(v.shape)} {q.dtype}")
+    if use_tc:
+        fmt = torch.channels_last
+        dout, q, k, v, out = (t.contiguous(memory_format=fmt) for t in (dout, q, k, v, out))
+        flags |= capi.CCA_FLAG_NHWC
+    else:
+        fmt = torch.contiguous_format
+        dout, q, k, v, out = (t.contiguous() for t in (dout, q, k, v, out))
+    lse = lse.contiguous()
     with torch.cuda.device(q.device):
-        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        dq = torch.empty_like(q, memory_format=fmt)
+        dk = torch.empty_like(k, memory_format=fmt)
+        dv = torch.empty_like(v, memory_format=fmt)
         nws = lib.cca_b200_workspace_bytes(capi.CCA_WS_BACKWARD, B, Cq, C, H, W, dt)
         ws = torch.empty((max(nws, 16),), dtype=torch.uint8, device=q.device)
         rc = lib.cca_b200_backward(dout.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
                                    lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
-                                   ws.data_ptr(), ws.numel(), B, Cq, C, H, W, dt,
-                                   capi.CCA_FLAG_FORCE_SIMT if impl == "simt" else capi.CCA_FLAG_AUTO,
+                                   ws.data_ptr(), ws.numel(), B, Cq, C, H, W, dt, flags,
                                    _stream_ptr(q.device))
     capi.check(rc, "cca_b200_backward")
     return dq, dk, dv
@@ -110,8 +125,7 @@ class _CCAFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         q, k, v, out, lse = ctx.saved_tensors
-        bimpl = "auto" if ctx.impl == "tc" else ctx.impl
-        dq, dk, dv = cca_backward(dout, q, k, v, out, lse, bimpl)
+        dq, dk, dv = cca_backward(dout, q, k, v, out, lse, ctx.impl)
         return dq, dk, dv, None
 
 
