@@ -1,14 +1,18 @@
 #!/usr/bin/env python
 """bench.py -- CCA hot-path benchmark (BASELINE.json metric).
 
-metric  : CCA fwd+bwd pixels/s @ B x 512 x 97 x 97, R=2  (pixels counted once per step)
-step    : one pass of the hot path over one synthetic batch = the drop-in
-          ``cc_attention.CrissCrossAttention`` module applied R=2 times (networks/ccnet.py:118-119)
-          forward + backward, fp32, B=8 per GPU (weak scaling: images are sharded across ranks,
-          the op needs no collective; DDP all-reduces the 7 parameter grads only).
-value   : x resident in HBM.          e2e : same step, x from pinned host memory, y and dx copied back.
-roofline: the CCA operator itself (all kernels of one op fwd+bwd step, our .so), algorithmic bytes of
-          SURVEY.md 8(d) over the CUDA-event time of those launches.
+metric  : CCA fwd+bwd pixels/s @ B x 512 x 97 x 97, R=2  (pixels counted once per step; SURVEY.md 8d)
+step    : one pass of the hot path over one synthetic batch = the criss-cross attention operator
+          (q,k,v -> out forward, dout -> dq,dk,dv backward; cc_attention/functions.py:30-47 and its autograd)
+          applied R=2 times in sequence (networks/ccnet.py:118-119), fp32, B=8 images per GPU.  Weak scaling:
+          images are sharded across ranks; the op needs no collective.
+value   : that op sequence with q,k,v,dout resident in HBM (the boundary SURVEY.md 8(d) defines the
+          algorithmic bytes on, so ``roofline`` describes exactly the timed kernels).
+e2e     : the same R=2 fwd+bwd through the user-facing drop-in ``cc_attention.CrissCrossAttention`` nn.Module
+          (stock-torch 1x1 Q/K/V convs + our op + residual; DDP grad all-reduce when N>1), x from pinned host
+          memory every step, y and dx copied back to pinned host memory.  ``module`` = same, x resident.
+roofline: all kernels of one op forward / backward (our .so), algorithmic bytes of SURVEY.md 8(d) over the
+          CUDA-event time of those launches (L2 flushed between iterations).
 --impl reference : the reference module's CPU path (oracle module port; the Python reference cannot
           travel to the GPU box) on the host cores, bounded sample of the same workload.
 """
@@ -158,8 +162,9 @@ def run_reference(args):
 
 
 def workload_name():
-    return (f"CrissCrossAttention module x R={CFG['R']} fwd+bwd, B={CFG['B']}/GPU C={CFG['C']} Cq={CFG['C'] // 8} "
-            f"{CFG['H']}x{CFG['W']} fp32 (BASELINE configs[1])")
+    return (f"criss-cross attention op x R={CFG['R']} fwd+bwd, B={CFG['B']}/GPU C={CFG['C']} Cq={CFG['C'] // 8} "
+            f"{CFG['H']}x{CFG['W']} fp32 (BASELINE configs[1]); e2e/reference arm: the CrissCrossAttention nn.Module "
+            f"(1x1 convs + op + residual) on the same shape")
 
 
 def time_events(fn, steps, warmup, barrier=None):
@@ -238,22 +243,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- main timed region (module level, resident) -----------------------------------------
-    n0 = capi.launch_count()
-    with ClockSampler(local_rank) as clk:
-        ms = time_events(step_resident, args.steps, args.warmup, barrier)
-    launches = (capi.launch_count() - n0) * args.steps // (args.steps + args.warmup)
-    ms = max_over_ranks(ms)
-    px = B * H * W * world
-    value = px / (ms * 1e-3)
-
-    # ---- e2e (host buffers) ---------------------------------------------------------------------
-    ms_e2e = max_over_ranks(time_events(step_e2e, max(3, args.steps // 2), 3, barrier))
-    e2e = {"value": px / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-           "h2d_bytes_per_step": x_host.numel() * esize, "d2h_bytes_per_step": 2 * x_host.numel() * esize,
-           "note": "x from pinned host memory; y and dx copied back to pinned host memory every step"}
-
-    # ---- operator-only timings (the kernels of this repo) -> roofline ---------------------------
+    # ---- operator tensors (resident), in the layout the selected kernels work on ---------------------
     q = torch.randn(B, Cq, H, W, device=dev, dtype=dtype) * 0.58
     k = torch.randn(B, Cq, H, W, device=dev, dtype=dtype) * 0.58
     v = torch.randn(B, C, H, W, device=dev, dtype=dtype) * 0.58
@@ -262,8 +252,33 @@ def run_ours(args):
     if args.kernels != "simt" and tc_eligible(B, Cq, C, H, W, dtype):
         # the tensor-core kernels are channels-last; hand them resident tensors in their own layout
         q, k, v, do = (t.contiguous(memory_format=torch.channels_last) for t in (q, k, v, do))
+    op_layout = "channels_last" if not q.is_contiguous() else "nchw"
+
+    def step_op():                                  # R sequential op applications, forward + backward
+        for _ in range(R):
+            out, lse = cca_forward(q, k, v, impl=args.kernels)
+            cca_backward(do, q, k, v, out, lse, impl=args.kernels)
+
+    # ---- main timed region: op level, resident ------------------------------------------------------
+    n0 = capi.launch_count()
+    with ClockSampler(local_rank) as clk:
+        ms = time_events(step_op, args.steps, args.warmup, barrier)
+    launches = (capi.launch_count() - n0) * args.steps // (args.steps + args.warmup)
+    ms = max_over_ranks(ms)
+    px = B * H * W * world
+    value = px / (ms * 1e-3)
+
+    # ---- module level: resident and e2e (host buffers) -----------------------------------------------
+    ms_mod = max_over_ranks(time_events(step_resident, max(3, args.steps // 2), 3, barrier))
+    module = {"value": px / (ms_mod * 1e-3), "unit": UNIT, "ms_per_step": ms_mod,
+              "note": "CrissCrossAttention nn.Module x R fwd+bwd, x resident; includes the stock-torch fp32 1x1 convs"}
+    ms_e2e = max_over_ranks(time_events(step_e2e, max(3, args.steps // 2), 3, barrier))
+    e2e = {"value": px / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+           "h2d_bytes_per_step": x_host.numel() * esize, "d2h_bytes_per_step": 2 * x_host.numel() * esize,
+           "note": "nn.Module x R fwd+bwd; x from pinned host memory; y and dx copied back to pinned host memory every step"}
+
+    # ---- per-op timings of the kernels of this repo -> roofline ----------------------------------------
     out, lse = cca_forward(q, k, v, impl=args.kernels)
-    bimpl = args.kernels
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > L2 (126 MB)
 
     def op_time(fn, iters=10):
@@ -285,9 +300,8 @@ def run_ours(args):
     f_avg, f_min = op_time(lambda: cca_forward(q, k, v, impl=args.kernels))
     nf = (capi.launch_count() - n1) // 13
     n1 = capi.launch_count()
-    b_avg, b_min = op_time(lambda: cca_backward(do, q, k, v, out, lse, impl=bimpl))
+    b_avg, b_min = op_time(lambda: cca_backward(do, q, k, v, out, lse, impl=args.kernels))
     nb = (capi.launch_count() - n1) // 13
-    op_layout = "channels_last" if q.is_contiguous(memory_format=torch.channels_last) and not q.is_contiguous() else "nchw"
     peak, peak_src = measured_peaks()
     bytes_f, bytes_b = alg_bytes(B, C, H, W, esize, True, False), alg_bytes(B, C, H, W, esize, False, True)
     dom_is_bwd = b_avg >= f_avg
@@ -301,7 +315,6 @@ def run_ours(args):
                            "frac": bytes_f / f_avg / 1e6 / peak, "launches": nf},
                 "op_bwd": {"ms": b_avg, "ms_min": b_min, "alg_bytes": bytes_b, "gbs": bytes_b / b_avg / 1e6,
                            "frac": bytes_b / b_avg / 1e6 / peak, "launches": nb},
-                "op_fwd_bwd_pixels_per_s_R2": B * H * W / (R * (f_avg + b_avg) * 1e-3),
                 "op_layout": op_layout,
                 "timing": "CUDA events on torch's current stream (the launching stream), L2 flushed between iterations"}
 
@@ -315,11 +328,12 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32" if dtype == torch.float32 else "bf16", "data": "synthetic",
                 "config": {"workload": workload_name(), "global_batch": B * world, "kernels": args.kernels,
-                           "l2": "working set (x,y,dy,q,k,v,out: >1 GB) exceeds the 126 MB L2; no explicit flush in "
-                                 "the module loop, explicit 256 MB flush between operator-only iterations",
+                           "op_layout": op_layout,
+                           "l2": "inputs larger than L2: one op fwd+bwd touches q,k,v,dout,out,dq,dk,dv = 1.04 GB vs 126 MB "
+                                 "L2 (no explicit flush in the timed loop); the per-op roofline timings flush 256 MB explicitly",
                            "parallelism": f"dp{world} (image-sharded, DDP grad all-reduce only)"},
-                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu}
+                "clocks": clk.summary(), "e2e": e2e, "module": module, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
