@@ -24,6 +24,8 @@ namespace {
 using namespace tc;
 
 constexpr int kTmemCols = 256;      // S / dP: [0,128)   O0: [128,192)   O1: [192,256)
+constexpr int kRegsSoft = 152, kRegsEpi = 144;
+static_assert(reg_pool_ok(kRegsSoft, kRegsEpi), "setmaxnreg pool");
 
 struct BwdParams {
     int B, H, W, C, Cq;
@@ -92,7 +94,11 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
         if (p.col) { cw = i; ch = 0; } else { cw = 0; ch = i; }
     };
 
-    if (warp == kWarpProducer) {
+    if (warp >= kWarpProducer) reg_dec<kRegsMisc>();
+    else if (warp >= kWarpConv0) reg_dec<kRegsConv>();
+    if (warp > kWarpMma) {
+        // idle padding warps
+    } else if (warp == kWarpProducer) {
         // =============================== TMA producer ===============================
         if (lane == 0) {
             uint32_t g = 0;
@@ -201,9 +207,9 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
             commit_to(&bars[B_P_EMPTY]);
             u += 2;
         }
-    } else if (warp >= 4) {
+    } else if (warp >= kWarpConv0) {
         // =============================== converters (256 threads) ===============================
-        const int t = tid - 128;
+        const int t = tid - kWarpConv0 * 32;
         uint32_t g = 0;
         for (int line = blockIdx.x; line < total_lines; line += gridDim.x) {
             for (int item = 0; item < NI; ++item, ++g) {
@@ -216,23 +222,12 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                 mbar_arrive(&bars[B_LD_EMPTY + slot]);
             }
         }
-    } else {
-        // =============================== P / dS + epilogues (128 threads, TMEM lane == pixel) ===============================
-        const int r = tid;
-        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
-        const bool elected = tid == 0;
-        uint32_t oc = 0, ln = 0;
-        // output item i of a line: i < NCH -> dV chunk i; NCH -> dQ; NCH+1 -> dK
-        auto out_map = [&](int i) -> const CUtensorMap * { return i < NCH ? &mdv : (i == NCH ? &mdq : &mdk); };
-        auto out_c0 = [&](int i) { return i < NCH ? i * kNC : 0; };
-        if (!p.col && elected) {                             // prefetch the partial of the very first output item
-            int cw, ch, cb;
-            line_coords(blockIdx.x, cw, ch, cb);
-            uint8_t *dst = smem + S::off_out;
-            mbar_expect_tx(&bars[B_OUT_FULL + 0], T::kSlot);
-            tma_load_4d(dst, out_map(0), &bars[B_OUT_FULL + 0], 0, cw, ch, cb);
-            tma_load_4d(dst + T::kTile, out_map(0), &bars[B_OUT_FULL + 0], 32, cw, ch, cb);
-        }
+    } else if (warp >= 4) {
+        // =============================== P / dS group (128 threads, TMEM lane == query pixel) ===============================
+        reg_inc<kRegsSoft>();
+        const int r = tid - 128;
+        const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t ln = 0;
         for (int line = blockIdx.x; line < total_lines; line += gridDim.x, ++ln) {
             int cw, ch, cb;
             line_coords(line, cw, ch, cb);
@@ -244,9 +239,89 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                 dl = p.delta[pix];
             }
             uint8_t *ph = smem + S::off_p + r * 16, *pl = ph + T::kPP * T::kPlane;
-
-            // one output item: TMEM accumulator -> (+ partial) -> swizzled staging -> TMA store
-            auto epilogue_item = [&](int i) {
+            // ---------------- P = exp(S - lse)
+            mbar_wait(&bars[B_S_FULL], ln & 1);
+            tc_fence_after();
+            {
+                float s[LK];
+#pragma unroll
+                for (int c0 = 0; c0 < LK; c0 += 16) tmem_ld16(tl + c0, reinterpret_cast<uint32_t *>(s + c0));
+                tmem_ld_wait();
+                tc_fence_before();
+#pragma unroll
+                for (int j = 0; j < LK; ++j) {
+                    const bool ok = rvalid && j < p.L && !(p.col && j == r);
+                    s[j] = ok ? exp2f(s[j] * kLog2e - lse2) : 0.f;
+                }
+                mbar_wait(&bars[B_P_EMPTY], (ln & 1) ^ 1);
+                if (r < LK) {
+#pragma unroll
+                    for (int kc = 0; kc < T::kPP; ++kc) {
+                        uint4 hi, lo;
+                        split8(s + kc * 8, hi, lo);
+                        *reinterpret_cast<uint4 *>(ph + kc * T::kPlane) = hi;
+                        *reinterpret_cast<uint4 *>(pl + kc * T::kPlane) = lo;
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(&bars[B_P_FULL]);
+            }
+            // ---------------- dS = P * (dP - delta)   (all MMAs that read P have completed: DP_FULL is committed after them)
+            mbar_wait(&bars[B_DP_FULL], ln & 1);
+            tc_fence_after();
+            {
+                float dp[LK];
+#pragma unroll
+                for (int c0 = 0; c0 < LK; c0 += 16) tmem_ld16(tl + c0, reinterpret_cast<uint32_t *>(dp + c0));
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&bars[B_S_EMPTY]);
+                if (r < LK) {
+#pragma unroll
+                    for (int kc = 0; kc < T::kPP; ++kc) {
+                        const uint4 hi = *reinterpret_cast<const uint4 *>(ph + kc * T::kPlane);
+                        const uint4 lo = *reinterpret_cast<const uint4 *>(pl + kc * T::kPlane);
+                        const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
+                        float ds[8];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float p0 = bf_lo(hw[e]) + bf_lo(lw[e]), p1 = bf_hi(hw[e]) + bf_hi(lw[e]);
+                            ds[2 * e] = p0 * (dp[kc * 8 + 2 * e] - dl);
+                            ds[2 * e + 1] = p1 * (dp[kc * 8 + 2 * e + 1] - dl);
+                        }
+                        uint4 dh, dlo;
+                        split8(ds, dh, dlo);
+                        *reinterpret_cast<uint4 *>(ph + kc * T::kPlane) = dh;
+                        *reinterpret_cast<uint4 *>(pl + kc * T::kPlane) = dlo;
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(&bars[B_DS_FULL]);
+            }
+        }
+    } else {
+        // =============================== epilogue group (128 threads, TMEM lane == output pixel) ===============================
+        reg_inc<kRegsEpi>();
+        const int r = tid;
+        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+        const bool elected = tid == 0;
+        uint32_t oc = 0;
+        // output item i of a line: i < NCH -> dV chunk i; NCH -> dQ; NCH+1 -> dK
+        auto out_map = [&](int i) -> const CUtensorMap * { return i < NCH ? &mdv : (i == NCH ? &mdq : &mdk); };
+        auto out_c0 = [&](int i) { return i < NCH ? i * kNC : 0; };
+        if (!p.col && elected) {                             // prefetch the partial of the very first output item
+            int cw, ch, cb;
+            line_coords(blockIdx.x, cw, ch, cb);
+            uint8_t *dst = smem + S::off_out;
+            mbar_expect_tx(&bars[B_OUT_FULL + 0], T::kSlot);
+            tma_load_4d(dst, out_map(0), &bars[B_OUT_FULL + 0], 0, cw, ch, cb);
+            tma_load_4d(dst + T::kTile, out_map(0), &bars[B_OUT_FULL + 0], 32, cw, ch, cb);
+        }
+        for (int line = blockIdx.x; line < total_lines; line += gridDim.x) {
+            int cw, ch, cb;
+            line_coords(line, cw, ch, cb);
+            for (int i = 0; i < NO; ++i, ++oc) {
+                // one output item: TMEM accumulator -> (+ partial) -> swizzled staging -> TMA store
                 const int os = oc & 1;
                 uint8_t *slot = smem + S::off_out + os * T::kSlot;
                 if (elected) {
@@ -294,73 +369,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                     tma_store_4d(out_map(i), slot + T::kTile, out_c0(i) + 32, cw, ch, cb);
                     tma_store_commit();
                 }
-                ++oc;
-            };
-
-            // ---------------- P = exp(S - lse)
-            mbar_wait(&bars[B_S_FULL], ln & 1);
-            tc_fence_after();
-            {
-                float s[LK];
-#pragma unroll
-                for (int c0 = 0; c0 < LK; c0 += 16) tmem_ld16(tl + c0, reinterpret_cast<uint32_t *>(s + c0));
-                tmem_ld_wait();
-                tc_fence_before();
-#pragma unroll
-                for (int j = 0; j < LK; ++j) {
-                    const bool ok = rvalid && j < p.L && !(p.col && j == r);
-                    s[j] = ok ? exp2f(s[j] * kLog2e - lse2) : 0.f;
-                }
-                mbar_wait(&bars[B_P_EMPTY], (ln & 1) ^ 1);
-                if (r < LK) {
-#pragma unroll
-                    for (int kc = 0; kc < T::kPP; ++kc) {
-                        uint4 hi, lo;
-                        split8(s + kc * 8, hi, lo);
-                        *reinterpret_cast<uint4 *>(ph + kc * T::kPlane) = hi;
-                        *reinterpret_cast<uint4 *>(pl + kc * T::kPlane) = lo;
-                    }
-                }
-                fence_proxy_async();
-                mbar_arrive(&bars[B_P_FULL]);
             }
-            // ---------------- dV chunks
-            for (int n = 0; n < NCH; ++n) epilogue_item(n);
-            // ---------------- dS = P * (dP - delta)   (all MMAs that read P have completed: DP_FULL is committed after them)
-            mbar_wait(&bars[B_DP_FULL], ln & 1);
-            tc_fence_after();
-            {
-                float dp[LK];
-#pragma unroll
-                for (int c0 = 0; c0 < LK; c0 += 16) tmem_ld16(tl + c0, reinterpret_cast<uint32_t *>(dp + c0));
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(&bars[B_S_EMPTY]);
-                if (r < LK) {
-#pragma unroll
-                    for (int kc = 0; kc < T::kPP; ++kc) {
-                        const uint4 hi = *reinterpret_cast<const uint4 *>(ph + kc * T::kPlane);
-                        const uint4 lo = *reinterpret_cast<const uint4 *>(pl + kc * T::kPlane);
-                        const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
-                        float ds[8];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float p0 = bf_lo(hw[e]) + bf_lo(lw[e]), p1 = bf_hi(hw[e]) + bf_hi(lw[e]);
-                            ds[2 * e] = p0 * (dp[kc * 8 + 2 * e] - dl);
-                            ds[2 * e + 1] = p1 * (dp[kc * 8 + 2 * e + 1] - dl);
-                        }
-                        uint4 dh, dlo;
-                        split8(ds, dh, dlo);
-                        *reinterpret_cast<uint4 *>(ph + kc * T::kPlane) = dh;
-                        *reinterpret_cast<uint4 *>(pl + kc * T::kPlane) = dlo;
-                    }
-                }
-                fence_proxy_async();
-                mbar_arrive(&bars[B_DS_FULL]);
-            }
-            // ---------------- dQ, dK
-            epilogue_item(NCH);
-            epilogue_item(NCH + 1);
         }
         if (elected) tma_store_wait_all<0>();
     }

@@ -11,14 +11,27 @@ using namespace sm100;
 
 constexpr int kNC = 64;   // channels per chunk (one ring slot = [LK px][64 ch] fp32 = two swizzled TMA tiles)
 
-// Thread layout of both kernels:
-//   warps 0-3   (128 thr) : TMEM group -- softmax / dS and the epilogues (TMEM lane == pixel)
-//   warps 4-11  (256 thr) : converters -- fp32 staging tile -> bf16 hi/lo operand planes
-//   warp 12               : TMA producer (one elected lane)
-//   warp 13               : MMA issuer (whole warp converged, tcgen05.mma under elect.sync)
-constexpr int kThreads = 448;
+// Thread layout of both kernels (five warpgroups, registers rebalanced with setmaxnreg):
+//   warps 0-3   (128 thr) : epilogue group        (TMEM lane == pixel; accumulators -> staging -> TMA store)
+//   warps 4-7   (128 thr) : softmax / P / dS group (TMEM lane == pixel)
+//   warps 8-15  (256 thr) : converters -- fp32 staging tile -> bf16 hi/lo operand planes
+//   warp 16               : TMA producer (one elected lane)
+//   warp 17               : MMA issuer (whole warp converged, tcgen05.mma under elect.sync)
+//   warps 18-19           : idle (pad the last warpgroup so setmaxnreg can release its registers)
+constexpr int kThreads = 640;
 constexpr int kConvThreads = 256;
-constexpr int kWarpProducer = 12, kWarpMma = 13;
+constexpr int kWarpConv0 = 8, kWarpProducer = 16, kWarpMma = 17;
+constexpr int kRegsConv = 56, kRegsMisc = 72;   // per kernel: kRegsSoft + kRegsEpi <= 296
+// setmaxnreg moves registers through a per-CTA pool that only holds what the CTA itself released: the increases must be
+// covered by the decreases relative to the launch allocation of 96 regs/thread (640 threads):
+//   released 256*(96-56) + 128*(96-72) = 13312  >=  claimed 128*(168-96) + 128*(128-96) = 13312
+constexpr bool reg_pool_ok(int soft, int epi)
+{
+    return 256 * (96 - kRegsConv) + 128 * (96 - kRegsMisc) >= 128 * (soft - 96) + 128 * (epi - 96);
+}
+
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 template <int LK> struct Tiles {
     static constexpr int kTile = LK * 128;             // [LK px][32 fp32], SWIZZLE_128B
@@ -96,6 +109,24 @@ __device__ __forceinline__ void mma_split3(uint32_t d, uint64_t ah, uint64_t al,
         mma_f16(d, ah, bh, idesc, accumulate);
         mma_f16(d, ah, bl, idesc, true);
         mma_f16(d, al, bh, idesc, true);
+    }
+    __syncwarp();
+}
+// Same, for a whole K loop: NK k-steps, descriptors advance by (a_step, b_step) bytes per step.  One election.
+template <int NK>
+__device__ __forceinline__ void mma_split3_loop(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t a_step, uint32_t a_lbo, uint32_t a_sbo,
+                                                uint32_t b_hi, uint32_t b_lo, uint32_t b_step, uint32_t b_lbo, uint32_t b_sbo,
+                                                uint32_t idesc, bool accumulate_first)
+{
+    if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < NK; ++ks) {
+            const uint64_t ah = smem_desc(a_hi + ks * a_step, a_lbo, a_sbo), al = smem_desc(a_lo + ks * a_step, a_lbo, a_sbo);
+            const uint64_t bh = smem_desc(b_hi + ks * b_step, b_lbo, b_sbo), bl = smem_desc(b_lo + ks * b_step, b_lbo, b_sbo);
+            mma_f16(d, ah, bh, idesc, accumulate_first || ks > 0);
+            mma_f16(d, ah, bl, idesc, true);
+            mma_f16(d, al, bh, idesc, true);
+        }
     }
     __syncwarp();
 }

@@ -8,14 +8,15 @@
 //
 // One persistent CTA per SM walks over lines.  Per line (L <= LK pixels, padded to LK):
 //   TMA producer (1 thread)   : 4-D tiled loads [LK px][32 ch] fp32, SWIZZLE_128B, OOB pixels zero-filled,
-//                               into a 2-slot ring: Q, K, then the V chunks (64 channels each).
+//                               into a 2-slot ring: Q, K of the NEXT line, then the V chunks (64 channels each)
+//                               of the current one (software pipeline across lines).
 //   converter warps (256 thr) : fp32 -> bf16 hi + bf16 lo split (x = hi + lo to ~2^-17), written as UMMA
 //                               canonical no-swizzle operand planes [8-channel chunk][pixel][16 B].
 //   MMA warp (elect.sync)     : S = Q K^T as 3 bf16 MMAs per k-step (hi*hi + hi*lo + lo*hi, fp32 accumulate
 //                               in TMEM, M=128 N=LK K=16), then per V chunk O = P V (M=128 N=64, K = pixels).
-//   softmax/epilogue (128 thr): TMEM -> registers (one query pixel per thread), exp2-based softmax, P split
-//                               hi/lo into K-major operand planes; per V chunk TMEM -> scale/merge ->
-//                               swizzled smem tile -> TMA store.
+//   softmax group (128 thr)   : TMEM -> registers (one query pixel per thread), exp2-based softmax, P split
+//                               hi/lo into K-major operand planes, per-pixel scales / stats / lse.
+//   epilogue group (128 thr)  : per V chunk TMEM -> scale/merge -> swizzled smem tile -> TMA store.
 // All inter-role hand-offs are mbarriers (TMA complete_tx, tcgen05.commit, thread arrives).
 #include "cca_tc_common.cuh"
 
@@ -24,6 +25,8 @@ namespace {
 using namespace tc;
 
 constexpr int kTmemCols = 256;      // S: [0,128)  O0: [128,192)  O1: [192,256)
+constexpr int kRegsSoft = 168, kRegsEpi = 128;
+static_assert(reg_pool_ok(kRegsSoft, kRegsEpi), "setmaxnreg pool");
 
 struct FwdParams {
     int B, H, W, C, Cq;
@@ -47,13 +50,17 @@ template <int LK> struct FwdSmem {
     static constexpr int off_op = off_out + 2 * T::kSlot; // 2 operand buffers
     static constexpr int off_p = off_op + 2 * T::kOp;
     static constexpr int off_tail = off_p + T::kP;        // 256 B pad: M=128 MMAs read 16 rows past LK rows
-    static constexpr int off_bar = off_tail + 256;
+    static constexpr int off_scale = off_tail + 256;      // float2 (sa, sb) [3][128]: softmax group -> epilogue group
+    static constexpr int off_bar = off_scale + 3 * 128 * 8;
     static constexpr int kBytes = off_bar + 256 + 1024;   // + alignment slack
 };
 
 enum { B_LD_FULL = 0, B_LD_EMPTY = 2, B_OP_FULL = 4, B_OP_EMPTY = 6, B_S_FULL = 8, B_S_EMPTY = 9, B_P_FULL = 10,
        B_P_EMPTY = 11, B_O_FULL = 12, B_O_EMPTY = 14, B_OUT_FULL = 16, B_COUNT = 18 };
 
+// Software pipeline across the lines k = 0..nk-1 of this CTA: the ring carries
+//     Q0 K0 | Q1 K1 V0[0..NCH) | Q2 K2 V1[0..NCH) | ...
+// so S(k+1) and its softmax run while P(k) V(k) is being accumulated and stored.
 template <int LK>
 __global__ void __launch_bounds__(kThreads, 1)
 cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
@@ -65,10 +72,12 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S::off_bar);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::off_bar + 8 * B_COUNT);
+    float2 *scale = reinterpret_cast<float2 *>(smem + S::off_scale);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NCH = p.C / kNC;
     const int KQ = p.Cq / 16;                 // k-steps of the S MMA
     const int total_lines = p.B * p.NL;
+    const int nk = (total_lines - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // lines of this CTA
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -94,118 +103,111 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
         const int i = line - cb * p.NL;
         if (p.col) { cw = i; ch = 0; } else { cw = 0; ch = i; }
     };
+    auto line_of = [&](int k) { return (int)blockIdx.x + k * (int)gridDim.x; };
 
-    if (warp == kWarpProducer) {
-        // =============================== TMA producer ===============================
-        if (lane == 0) {
-            uint32_t g = 0;
-            int dbg_n = 0;
-            for (int line = blockIdx.x; line < total_lines; line += gridDim.x) {
-                int cw, ch, cb;
-                line_coords(line, cw, ch, cb);
-                for (int item = 0; item < 2 + NCH; ++item, ++g) {
+    if (warp >= kWarpProducer) {
+        reg_dec<kRegsMisc>();
+        if (warp == kWarpProducer) {
+            // =============================== TMA producer ===============================
+            if (lane == 0) {
+                uint32_t g = 0;
+                int dbg_n = 0;
+                auto emit = [&](const CUtensorMap *m, int c0, int line) {
+                    int cw, ch, cb;
+                    line_coords(line, cw, ch, cb);
                     const int slot = g & 1;
                     mbar_wait(&bars[B_LD_EMPTY + slot], ((g >> 1) & 1) ^ 1);
                     CCA_STAMP(0);
                     uint8_t *dst = smem + S::off_ld + slot * T::kSlot;
                     mbar_expect_tx(&bars[B_LD_FULL + slot], T::kSlot);
-                    const CUtensorMap *m = item == 0 ? &mq : (item == 1 ? &mk : &mv);
-                    const int c0 = item < 2 ? 0 : (item - 2) * kNC;
                     tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, cb);
                     tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, cb);
+                    ++g;
+                };
+                emit(&mq, 0, line_of(0));
+                emit(&mk, 0, line_of(0));
+                for (int k = 0; k < nk; ++k) {
+                    if (k + 1 < nk) { emit(&mq, 0, line_of(k + 1)); emit(&mk, 0, line_of(k + 1)); }
+                    for (int n = 0; n < NCH; ++n) emit(&mv, n * kNC, line_of(k));
                 }
             }
-        }
-    } else if (warp == kWarpMma) {
-        // =============================== MMA issuer (whole warp, elect.sync inside) ===============================
-        const uint32_t idesc_s = instr_desc(kFmtBF16, kFmtBF16, 128, LK, false, false);
-        const uint32_t idesc_o = instr_desc(kFmtBF16, kFmtBF16, 128, kNC, false, true);
-        const uint32_t op_base = smem_u32(smem + S::off_op), p_base = smem_u32(smem + S::off_p);
-        uint32_t u = 0, oc = 0, ln = 0;
-        int dbg_n = lane == 0 ? 0 : 512;
-        for (int line = blockIdx.x; line < total_lines; line += gridDim.x, ++ln) {
-            // ---- S = Q K^T  (Q in operand buffer u&1, K in (u+1)&1)
-            const uint32_t qb = op_base + (u & 1) * T::kOp, kb = op_base + ((u + 1) & 1) * T::kOp;
-            mbar_wait(&bars[B_OP_FULL + (u & 1)], (u >> 1) & 1);
-            mbar_wait(&bars[B_OP_FULL + ((u + 1) & 1)], ((u + 1) >> 1) & 1);
-            mbar_wait(&bars[B_S_EMPTY], (ln & 1) ^ 1);
-            tc_fence_after();
-            CCA_STAMP(2);
-            for (int ks = 0; ks < KQ; ++ks) {
-                const uint32_t ao = ks * 2 * T::kPlane;
-                mma_split3(tmem, smem_desc(qb + ao, T::kPlane, 128), smem_desc(qb + 8 * T::kPlane + ao, T::kPlane, 128),
-                           smem_desc(kb + ao, T::kPlane, 128), smem_desc(kb + 8 * T::kPlane + ao, T::kPlane, 128),
-                           idesc_s, ks > 0);
-            }
-            commit_to(&bars[B_S_FULL]);
-            commit_to(&bars[B_OP_EMPTY + (u & 1)]);
-            commit_to(&bars[B_OP_EMPTY + ((u + 1) & 1)]);
-            u += 2;
-            // ---- O chunks = P V
-            CCA_STAMP(2);
-            mbar_wait(&bars[B_P_FULL], ln & 1);
-            CCA_STAMP(2);
-            for (int n = 0; n < NCH; ++n, ++u, ++oc) {
-                const uint32_t vb = op_base + (u & 1) * T::kOp;
+        } else if (warp == kWarpMma) {
+            // =============================== MMA issuer (whole warp, elect.sync inside) ===============================
+            const uint32_t idesc_s = instr_desc(kFmtBF16, kFmtBF16, 128, LK, false, false);
+            const uint32_t idesc_o = instr_desc(kFmtBF16, kFmtBF16, 128, kNC, false, true);
+            const uint32_t op_base = smem_u32(smem + S::off_op), p_base = smem_u32(smem + S::off_p);
+            uint32_t u = 0, oc = 0;
+            int dbg_n = lane == 0 ? 0 : 512;
+            auto issue_s = [&](int k) {            // S(k) = Q K^T, Q in operand buffer u&1, K in (u+1)&1
+                const uint32_t qb = op_base + (u & 1) * T::kOp, kb = op_base + ((u + 1) & 1) * T::kOp;
                 mbar_wait(&bars[B_OP_FULL + (u & 1)], (u >> 1) & 1);
-                mbar_wait(&bars[B_O_EMPTY + (oc & 1)], ((oc >> 1) & 1) ^ 1);
+                mbar_wait(&bars[B_OP_FULL + ((u + 1) & 1)], ((u + 1) >> 1) & 1);
+                mbar_wait(&bars[B_S_EMPTY], (k & 1) ^ 1);
                 tc_fence_after();
                 CCA_STAMP(2);
-                const uint32_t d = tmem + 128 + (oc & 1) * kNC;
-#pragma unroll
-                for (int ks = 0; ks < LK / 16; ++ks) {
-                    const uint32_t ao = ks * 2 * T::kPlane, bo = ks * 256;
-                    mma_split3(d, smem_desc(p_base + ao, T::kPlane, 128), smem_desc(p_base + T::kPP * T::kPlane + ao, T::kPlane, 128),
-                               smem_desc(vb + bo, 128, T::kPlane), smem_desc(vb + 8 * T::kPlane + bo, 128, T::kPlane),
-                               idesc_o, ks > 0);
+                for (int ks = 0; ks < KQ; ++ks) {
+                    const uint32_t ao = ks * 2 * T::kPlane;
+                    mma_split3(tmem, smem_desc(qb + ao, T::kPlane, 128), smem_desc(qb + 8 * T::kPlane + ao, T::kPlane, 128),
+                               smem_desc(kb + ao, T::kPlane, 128), smem_desc(kb + 8 * T::kPlane + ao, T::kPlane, 128),
+                               idesc_s, ks > 0);
                 }
-                commit_to(&bars[B_O_FULL + (oc & 1)]);
+                commit_to(&bars[B_S_FULL]);
                 commit_to(&bars[B_OP_EMPTY + (u & 1)]);
+                commit_to(&bars[B_OP_EMPTY + ((u + 1) & 1)]);
+                u += 2;
+            };
+            issue_s(0);
+            for (int k = 0; k < nk; ++k) {
+                if (k + 1 < nk) issue_s(k + 1);
                 CCA_STAMP(2);
+                mbar_wait(&bars[B_P_FULL], k & 1);
+                CCA_STAMP(2);
+                for (int n = 0; n < NCH; ++n, ++u, ++oc) {
+                    const uint32_t vb = op_base + (u & 1) * T::kOp;
+                    mbar_wait(&bars[B_OP_FULL + (u & 1)], (u >> 1) & 1);
+                    mbar_wait(&bars[B_O_EMPTY + (oc & 1)], ((oc >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    CCA_STAMP(2);
+                    mma_split3_loop<LK / 16>(tmem + 128 + (oc & 1) * kNC,
+                                             p_base, p_base + T::kPP * T::kPlane, 2 * T::kPlane, T::kPlane, 128,
+                                             vb, vb + 8 * T::kPlane, 256, 128, T::kPlane, idesc_o, false);
+                    commit_to(&bars[B_O_FULL + (oc & 1)]);
+                    commit_to(&bars[B_OP_EMPTY + (u & 1)]);
+                    CCA_STAMP(2);
+                }
+                commit_to(&bars[B_P_EMPTY]);
             }
-            commit_to(&bars[B_P_EMPTY]);
+        }
+    } else if (warp >= kWarpConv0) {
+        // =============================== converters (256 threads) ===============================
+        reg_dec<kRegsConv>();
+        const int t = tid - kWarpConv0 * 32;
+        const uint32_t total_items = (uint32_t)nk * (2 + NCH);
+        int dbg_n = t == 0 ? 0 : 512;
+        for (uint32_t g = 0; g < total_items; ++g) {
+            const int slot = g & 1, ob = g & 1;
+            mbar_wait(&bars[B_LD_FULL + slot], (g >> 1) & 1);
+            CCA_STAMP(1);
+            mbar_wait(&bars[B_OP_EMPTY + ob], ((g >> 1) & 1) ^ 1);
+            CCA_STAMP(1);
+            convert_slot<LK>(smem + S::off_ld + slot * T::kSlot, smem + S::off_op + ob * T::kOp, t);
+            fence_proxy_async();
+            mbar_arrive(&bars[B_OP_FULL + ob]);
+            mbar_arrive(&bars[B_LD_EMPTY + slot]);
+            CCA_STAMP(1);
         }
     } else if (warp >= 4) {
-        // =============================== converters (256 threads) ===============================
-        const int t = tid - 128;
-        uint32_t g = 0;
-        int dbg_n = t == 0 ? 0 : 512;
-        for (int line = blockIdx.x; line < total_lines; line += gridDim.x) {
-            for (int item = 0; item < 2 + NCH; ++item, ++g) {
-                const int slot = g & 1, ob = g & 1;
-                mbar_wait(&bars[B_LD_FULL + slot], (g >> 1) & 1);
-                CCA_STAMP(1);
-                mbar_wait(&bars[B_OP_EMPTY + ob], ((g >> 1) & 1) ^ 1);
-                CCA_STAMP(1);
-                convert_slot<LK>(smem + S::off_ld + slot * T::kSlot, smem + S::off_op + ob * T::kOp, t);
-                fence_proxy_async();
-                mbar_arrive(&bars[B_OP_FULL + ob]);
-                mbar_arrive(&bars[B_LD_EMPTY + slot]);
-                CCA_STAMP(1);
-            }
-        }
-    } else {
-        // =============================== softmax + epilogue (128 threads, TMEM lane == pixel) ===============================
-        const int r = tid;                                   // query pixel of this thread
-        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
-        const bool elected = tid == 0;
-        uint32_t oc = 0, ln = 0;
-        int dbg_n = tid == 0 ? 0 : 512;
-        if (!p.col && elected) {                             // prefetch the partial of the very first chunk
+        // =============================== softmax group (128 threads, TMEM lane == query pixel) ===============================
+        reg_inc<kRegsSoft>();
+        const int r = tid - 128;
+        const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        int dbg_n = r == 0 ? 0 : 512;
+        for (int k = 0; k < nk; ++k) {
             int cw, ch, cb;
-            line_coords(blockIdx.x, cw, ch, cb);
-            uint8_t *dst = smem + S::off_out;
-            mbar_expect_tx(&bars[B_OUT_FULL + 0], T::kSlot);
-            tma_load_4d(dst, &mo, &bars[B_OUT_FULL + 0], 0, cw, ch, cb);
-            tma_load_4d(dst + T::kTile, &mo, &bars[B_OUT_FULL + 0], 32, cw, ch, cb);
-        }
-        for (int line = blockIdx.x; line < total_lines; line += gridDim.x, ++ln) {
-            int cw, ch, cb;
-            line_coords(line, cw, ch, cb);
+            line_coords(line_of(k), cw, ch, cb);
             const bool rvalid = r < p.L;
-            // ---------------- softmax of row r
             CCA_STAMP(3);
-            mbar_wait(&bars[B_S_FULL], ln & 1);
+            mbar_wait(&bars[B_S_FULL], k & 1);
             tc_fence_after();
             CCA_STAMP(3);
             float s[LK];
@@ -242,9 +244,10 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                     p.lse[pix] = mm + logf(lt);
                 }
             }
+            scale[(k % 3) * 128 + r] = make_float2(sa, sb);     // read by the epilogue group after O_FULL of line k
             // ---------------- P -> operand planes [key chunk][query pixel][16 B] (hi, lo)
             CCA_STAMP(3);
-            mbar_wait(&bars[B_P_EMPTY], (ln & 1) ^ 1);
+            mbar_wait(&bars[B_P_EMPTY], (k & 1) ^ 1);
             if (r < LK) {
                 uint8_t *ph = smem + S::off_p + r * 16, *pl = ph + T::kPP * T::kPlane;
 #pragma unroll
@@ -258,7 +261,27 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
             fence_proxy_async();
             mbar_arrive(&bars[B_P_FULL]);
             CCA_STAMP(3);
-            // ---------------- epilogue per V chunk
+        }
+    } else {
+        // =============================== epilogue group (128 threads, TMEM lane == query pixel) ===============================
+        reg_inc<kRegsEpi>();
+        const int r = tid;
+        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+        const bool elected = tid == 0;
+        uint32_t oc = 0;
+        int dbg_n = 512;
+        if (!p.col && elected) {                             // prefetch the partial of the very first chunk
+            int cw, ch, cb;
+            line_coords(line_of(0), cw, ch, cb);
+            uint8_t *dst = smem + S::off_out;
+            mbar_expect_tx(&bars[B_OUT_FULL + 0], T::kSlot);
+            tma_load_4d(dst, &mo, &bars[B_OUT_FULL + 0], 0, cw, ch, cb);
+            tma_load_4d(dst + T::kTile, &mo, &bars[B_OUT_FULL + 0], 32, cw, ch, cb);
+        }
+        for (int k = 0; k < nk; ++k) {
+            int cw, ch, cb;
+            line_coords(line_of(k), cw, ch, cb);
+            float sa = 0.f, sb = 0.f;
             for (int n = 0; n < NCH; ++n, ++oc) {
                 const int os = oc & 1;
                 uint8_t *slot = smem + S::off_out + os * T::kSlot;
@@ -268,11 +291,11 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                         mbar_arrive(&bars[B_OUT_FULL + os]);
                     } else {
                         tma_store_wait_read<0>();              // other slot drained -> prefetch next chunk's partial into it
-                        int nline = line, nn = n + 1;
-                        if (nn == NCH) { nn = 0; nline = line + gridDim.x; }
-                        if (nline < total_lines) {
+                        int nk2 = k, nn = n + 1;
+                        if (nn == NCH) { nn = 0; nk2 = k + 1; }
+                        if (nk2 < nk) {
                             int w2, h2, b2;
-                            line_coords(nline, w2, h2, b2);
+                            line_coords(line_of(nk2), w2, h2, b2);
                             uint8_t *dst = smem + S::off_out + (os ^ 1) * T::kSlot;
                             mbar_expect_tx(&bars[B_OUT_FULL + (os ^ 1)], T::kSlot);
                             tma_load_4d(dst, &mo, &bars[B_OUT_FULL + (os ^ 1)], nn * kNC, w2, h2, b2);
@@ -280,12 +303,10 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                         }
                     }
                 }
-                CCA_STAMP(3);
                 mbar_wait(&bars[B_OUT_FULL + os], (oc >> 1) & 1);
-                CCA_STAMP(3);
                 mbar_wait(&bars[B_O_FULL + os], (oc >> 1) & 1);
                 tc_fence_after();
-                CCA_STAMP(3);
+                if (n == 0) { const float2 sc = scale[(k % 3) * 128 + r]; sa = sc.x; sb = sc.y; }
                 float o[kNC];
 #pragma unroll
                 for (int c0 = 0; c0 < kNC; c0 += 16) tmem_ld16(tl + 128 + os * kNC + c0, reinterpret_cast<uint32_t *>(o + c0));
@@ -313,10 +334,10 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                     tma_store_4d(&mo, slot + T::kTile, n * kNC + 32, cw, ch, cb);
                     tma_store_commit();
                 }
-                CCA_STAMP(3);
             }
         }
         if (elected) tma_store_wait_all<0>();
+        (void)dbg_n;
     }
     tc_fence_before();
     __syncthreads();
