@@ -42,6 +42,8 @@ extern "C" {
 int cca_b200_version(void) { return CCA_B200_VERSION; }
 // profiling aid (not declared in the public header): device buffer of 2 x 4 x 512 int64 clock stamps
 CCA_API void cca_b200__set_debug_buffer(void *p) { set_tc_debug_buffer(p); }
+// A/B aid: run the tensor-core forward as two launches (column pass, row pass) instead of the fused launch
+CCA_API void cca_b200__set_two_pass(int on) { set_tc_two_pass(on); }
 const char *cca_b200_last_error(void) { return g_err; }
 const char *cca_b200_strerror(int s)
 {
@@ -77,8 +79,10 @@ size_t cca_b200_workspace_bytes(int which, int B, int Cq, int C, int H, int W, i
 {
     (void)Cq; (void)C; (void)dtype;
     const size_t pix = (size_t)B * H * W;
-    // forward: per-pixel (m,l) of the column pass; backward: per-pixel delta = <dout, out>
-    return which == CCA_WS_FORWARD ? pix * sizeof(float2) : pix * sizeof(float);
+    // forward: per-pixel (m,l) of the column pass + per-sample completion counters of the fused launch;
+    // backward: per-pixel delta = <dout, out> + the same counters
+    const size_t counters = (((size_t)B * sizeof(unsigned int)) + 15) & ~(size_t)15;
+    return (which == CCA_WS_FORWARD ? pix * sizeof(float2) : pix * sizeof(float)) + counters;
 }
 
 int cca_b200_forward(const void *q, const void *k, const void *v, void *out, float *lse, void *ws, size_t ws_bytes,

@@ -21,7 +21,7 @@ __device__ __forceinline__ uint32_t plane_off(int row, int chunk, int rows) { re
 // P: [128][KP] fp32; V: [KP][N2] fp32 (row = k, MN contiguous);           D2 = P * V      [128][N2]
 template <int KA, int N1, int KP, int N2>
 __global__ void __launch_bounds__(128) umma_probe(const float *A, const float *B1, const float *P, const float *V,
-                                                  float *D1, float *D2)
+                                                  float *D1, float *D2, float *D3)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(128) umma_probe(const float *A, const float *B
     uint8_t *sV = sP + (KP / 8) * 128 * 16;   // (N2/8) planes x KP rows
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
-    if (warp == 0) tmem_alloc<256>(&tmem_base_s);
+    if (warp == 0) tmem_alloc<512>(&tmem_base_s);
     // convert + store operands (bf16, plane layout)
     auto put = [](uint8_t *base, int row, int chunk, int rows, const float *src) {
         __nv_bfloat16 v[8];
@@ -63,6 +63,29 @@ __global__ void __launch_bounds__(128) umma_probe(const float *A, const float *B
             uint64_t bd = smem_desc(smem_u32(sV) + ks * 16 * 16, 128, KP * 16);
             mma_f16(tmem + 128, ad, bd, id2, ks > 0);
         }
+    }
+    // D3 = P * V with A = P held in TMEM (bf16 pairs, low half = even k), B = V planes (MN-major) from smem
+    {
+        const uint32_t lane_b = (uint32_t)(warp * 32) << 16;
+        for (int c0 = 0; c0 < KP / 2; c0 += 8) {
+            uint32_t w[8];
+            for (int i = 0; i < 8; ++i) {
+                __nv_bfloat162 v2 = __floats2bfloat162_rn(P[tid * KP + 2 * (c0 + i)], P[tid * KP + 2 * (c0 + i) + 1]);
+                w[i] = *reinterpret_cast<uint32_t *>(&v2);
+            }
+            tmem_st8(tmem + 192 + lane_b + c0, w);
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+        constexpr uint32_t id3 = instr_desc(kFmtBF16, kFmtBF16, 128, N2, false, true);
+        for (int ks = 0; ks < KP / 16; ++ks) {
+            uint64_t bd = smem_desc(smem_u32(sV) + ks * 16 * 16, 128, KP * 16);
+            mma_f16_ts(tmem + 320, tmem + 192 + ks * 8, bd, id3, ks > 0);
+        }
         mma_commit(&bar);
     }
     mbar_wait(&bar, 0);
@@ -79,9 +102,14 @@ __global__ void __launch_bounds__(128) umma_probe(const float *A, const float *B
         tmem_ld_wait();
         for (int i = 0; i < 16; ++i) D2[tid * N2 + c0 + i] = __uint_as_float(r[i]);
     }
+    for (int c0 = 0; c0 < N2; c0 += 16) {
+        tmem_ld16(tmem + 320 + lane_base + c0, r);
+        tmem_ld_wait();
+        for (int i = 0; i < 16; ++i) D3[tid * N2 + c0 + i] = __uint_as_float(r[i]);
+    }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<256>(tmem);
+    if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
 // TMA probe: load a row box and a column box of an NHWC fp32 tensor with SWIZZLE_128B, dump raw smem, store back.
@@ -123,16 +151,17 @@ int main()
     srand(1);
     auto rnd = [] { return (float)(rand() % 2001 - 1000) / 1000.f; };
     for (auto &x : A) x = rnd(); for (auto &x : B1) x = rnd(); for (auto &x : P) x = rnd(); for (auto &x : V) x = rnd();
-    float *dA, *dB1, *dP, *dV, *dD1, *dD2;
+    float *dA, *dB1, *dP, *dV, *dD1, *dD2, *dD3;
     CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB1, B1.size() * 4)); CK(cudaMalloc(&dP, P.size() * 4)); CK(cudaMalloc(&dV, V.size() * 4));
-    CK(cudaMalloc(&dD1, 128 * N1 * 4)); CK(cudaMalloc(&dD2, 128 * N2 * 4));
+    CK(cudaMalloc(&dD1, 128 * N1 * 4)); CK(cudaMalloc(&dD2, 128 * N2 * 4)); CK(cudaMalloc(&dD3, 128 * N2 * 4));
     CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB1, B1.data(), B1.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dP, P.data(), P.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dV, V.data(), V.size() * 4, cudaMemcpyHostToDevice));
     size_t smem = (KA / 8) * 128 * 16 + (KA / 8) * N1 * 16 + (KP / 8) * 128 * 16 + (N2 / 8) * KP * 16;
     CK(cudaFuncSetAttribute(umma_probe<KA, N1, KP, N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_probe<KA, N1, KP, N2><<<1, 128, smem>>>(dA, dB1, dP, dV, dD1, dD2);
+    umma_probe<KA, N1, KP, N2><<<1, 128, smem>>>(dA, dB1, dP, dV, dD1, dD2, dD3);
     CK(cudaDeviceSynchronize());
-    std::vector<float> D1(128 * N1), D2(128 * N2);
+    std::vector<float> D1(128 * N1), D2(128 * N2), D3(128 * N2);
+    CK(cudaMemcpy(D3.data(), dD3, D3.size() * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(D1.data(), dD1, D1.size() * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(D2.data(), dD2, D2.size() * 4, cudaMemcpyDeviceToHost));
     auto bf = [](float x) { return __bfloat162float(__float2bfloat16_rn(x)); };
     double e1 = 0, e2 = 0;
@@ -144,6 +173,9 @@ int main()
         double s = 0; for (int k = 0; k < KP; ++k) s += (double)bf(P[m * KP + k]) * bf(V[k * N2 + n]);
         e2 = fmax(e2, fabs(s - D2[m * N2 + n]));
     }
+    double e3 = 0;
+    for (size_t i = 0; i < D3.size(); ++i) e3 = fmax(e3, fabs((double)D3[i] - D2[i]));
+    printf("UMMA A-from-TMEM (tcgen05.st bf16 pairs, low half = even k) vs SS result: max abs diff %.3e  %s\n", e3, e3 < 1e-3 ? "OK" : "MISMATCH");
     printf("UMMA K-major x K-major  (M128 N%d K%d): max abs err %.3e  %s\n", N1, KA, e1, e1 < 1e-3 ? "OK" : "MISMATCH");
     printf("UMMA K-major x MN-major (M128 N%d K%d): max abs err %.3e  %s\n", N2, KP, e2, e2 < 1e-3 ? "OK" : "MISMATCH");
 
