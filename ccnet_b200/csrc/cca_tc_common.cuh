@@ -17,10 +17,11 @@ constexpr int kNC = 64;   // channels per chunk (one ring slot = [LK px][64 ch] 
 //   warps 8-15  (256 thr) : converters -- fp32 staging tile -> bf16 hi/lo operand planes
 //   warp 16               : TMA producer (one elected lane)
 //   warp 17               : MMA issuer (whole warp converged, tcgen05.mma under elect.sync)
-//   warps 18-19           : idle (pad the last warpgroup so setmaxnreg can release its registers)
+//   warp 18               : store warp (one lane): staging slots <-> global (TMA stores, partial prefetch, publishing)
+//   warp 19               : idle (pads the last warpgroup so setmaxnreg can release its registers)
 constexpr int kThreads = 640;
 constexpr int kConvThreads = 256;
-constexpr int kWarpConv0 = 8, kWarpProducer = 16, kWarpMma = 17;
+constexpr int kWarpConv0 = 8, kWarpProducer = 16, kWarpMma = 17, kWarpStore = 18;
 constexpr int kRegsConv = 56, kRegsMisc = 72;   // per kernel: kRegsSoft + kRegsEpi <= 296
 // setmaxnreg moves registers through a per-CTA pool that only holds what the CTA itself released: the increases must be
 // covered by the decreases relative to the launch allocation of 96 regs/thread (640 threads):

@@ -6,11 +6,11 @@
 //   column items (self entry masked, functions.py:38): out <- V P_c / l_c, stats <- (m_c, l_c)
 //   row items    (functions.py:39): flash-style merge with the column result -> out, lse  (functions.py:40-47)
 //
-// ONE persistent launch processes both kinds of items: the item list is  col(b=0) row(0) col(1) row(1) ...
-// (all column lines of a sample, then its row lines), CTA c takes items c, c+grid, ...  A row line of
+// ONE persistent launch processes both kinds of items: the item list is  col(0) | col(1) row(0) | col(2) row(1) ...
+// (all column lines of a sample; its row lines one block later), CTA c takes items c, c+grid, ...  A row line of
 // sample b needs every column line of b: column items bump a per-sample counter after their last TMA store
 // has completed; row items spin on it (all earlier items are owned by running CTAs, so this cannot deadlock).
-// Scheduling a sample's rows right after its columns keeps q,k,v and the partial output in the 126 MB L2.
+// Scheduling a sample's rows shortly after its columns keeps q,k,v and the partial output in the 126 MB L2.
 //
 // Roles (warpgroups, registers rebalanced with setmaxnreg), software-pipelined across items:
 //   TMA producer (1 thread)   : 4-D tiled loads [LK px][32 ch] fp32, SWIZZLE_128B, OOB pixels zero-filled,
@@ -58,11 +58,17 @@ __device__ __forceinline__ Item decode_item(const FwdParams &p, int idx)
 {
     Item it;
     if (p.mode == MODE_FUSED) {
-        const int per = p.W + p.H;
-        it.b = idx / per;
-        const int rem = idx - it.b * per;
-        it.col = rem < p.W;
-        it.i = it.col ? rem : rem - p.W;
+        // order: col(0) | col(1) row(0) | col(2) row(1) | ... | row(B-1)  -- the rows of a sample trail its columns by one
+        // block of column lines, so a row line (almost) never has to wait for the column lines it depends on, while
+        // the partial output and q,k,v of the sample are still in L2
+        if (idx < p.W) { it.col = 1; it.b = 0; it.i = idx; }
+        else {
+            const int per = p.W + p.H, x = idx - p.W;
+            const int j = x / per, rem = x - j * per;
+            if (j < p.B - 1 && rem < p.W) { it.col = 1; it.b = j + 1; it.i = rem; }
+            else if (j < p.B - 1) { it.col = 0; it.b = j; it.i = rem - p.W; }
+            else { it.col = 0; it.b = p.B - 1; it.i = rem; }
+        }
     } else {
         it.col = p.mode == MODE_COL_ONLY;
         const int nl = it.col ? p.W : p.H;
@@ -86,12 +92,12 @@ template <int LK> struct FwdSmem {
     static constexpr int off_tail = off_op + 2 * T::kOp;      // 256 B pad: M=128 MMAs read 16 rows past LK rows
     static constexpr int off_scale = off_tail + 256;          // float2 (sa, sb) [2][128]: softmax group -> epilogue group
     static constexpr int off_bar = off_scale + 2 * 128 * 8;
-    static constexpr int kBytes = off_bar + 256;
+    static constexpr int kBytes = off_bar + 320;
     static_assert(kBytes <= 232448, "shared memory budget");
 };
 
 enum { B_LD_FULL = 0, B_LD_EMPTY = 3, B_OP_FULL = 6, B_OP_EMPTY = 8, B_S_FULL = 10, B_S_EMPTY = 11, B_P_FULL = 12,
-       B_P_EMPTY = 13, B_O_FULL = 14, B_O_EMPTY = 18, B_OUT_FULL = 22, B_SC_EMPTY = 25, B_SC_FULL = 27, B_COUNT = 29 };
+       B_P_EMPTY = 13, B_O_FULL = 14, B_O_EMPTY = 18, B_OUT_FULL = 22, B_SC_EMPTY = 25, B_SC_FULL = 27, B_STAGED = 29, B_COUNT = 32 };
 
 __device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p)
 {
@@ -132,7 +138,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
         for (int i = 0; i < kNLd; ++i) { mbar_init(&bars[B_LD_FULL + i], 1); mbar_init(&bars[B_LD_EMPTY + i], kConvThreads); }
         for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_OP_FULL + i], kConvThreads); mbar_init(&bars[B_OP_EMPTY + i], 1); }
         for (int i = 0; i < kNOB; ++i) { mbar_init(&bars[B_O_FULL + i], 1); mbar_init(&bars[B_O_EMPTY + i], 128); }
-        for (int i = 0; i < kNOut; ++i) mbar_init(&bars[B_OUT_FULL + i], 1);
+        for (int i = 0; i < kNOut; ++i) { mbar_init(&bars[B_OUT_FULL + i], 1); mbar_init(&bars[B_STAGED + i], 128); }
         for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_SC_EMPTY + i], 128); mbar_init(&bars[B_SC_FULL + i], 128); }
         mbar_init(&bars[B_S_FULL], 1); mbar_init(&bars[B_S_EMPTY], 128);
         mbar_init(&bars[B_P_FULL], 128); mbar_init(&bars[B_P_EMPTY], 1);
@@ -235,6 +241,65 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                 }
                 commit_to(&bars[B_P_EMPTY]);
             }
+        } else if (warp == kWarpStore) {
+            // =============================== store warp (one lane): staging slots <-> global ===============================
+            // Per output chunk c (slot c % kNOut): make the slot ready for the epilogue group (a row item gets its column
+            // partial prefetched by TMA, two chunks ahead), and once the group has staged the merged tile, TMA-store it.
+            // Column items are published (per-sample counter) after their last store has completed.
+            if (lane == 0) {
+                const uint32_t total_chunks = (uint32_t)nk * NCH;
+                uint32_t prep = 0;                         // chunks prepared so far
+                int pub_k = 0;                             // items [0, pub_k) are published / need no publishing
+                auto chunk_item = [&](uint32_t c) { return (int)(c / NCH); };
+                auto can_prepare = [&](uint32_t c) {       // a row chunk must not wait for a column item this warp has yet to publish
+                    const Item nx = item_of(chunk_item(c));
+                    if (nx.col || p.mode != MODE_FUSED) return true;
+                    for (int j = pub_k; j < chunk_item(c); ++j) {
+                        const Item pj = item_of(j);
+                        if (pj.col && pj.b == nx.b) return false;
+                    }
+                    return true;
+                };
+                auto prepare = [&](uint32_t c) {
+                    const Item it = item_of(chunk_item(c));
+                    const int n = c % NCH, os = c % kNOut;
+                    if (it.col) { mbar_arrive(&bars[B_OUT_FULL + os]); return; }
+                    if (p.mode == MODE_FUSED) { wait_done(p.done + it.b, (unsigned)p.W); fence_proxy_async_all(); }
+                    uint8_t *dst = smem + S::off_out + os * T::kSlot;
+                    mbar_expect_tx(&bars[B_OUT_FULL + os], T::kSlot);
+                    tma_load_4d(dst, &mor, &bars[B_OUT_FULL + os], n * kNC, 0, it.i, it.b);
+                    tma_load_4d(dst + T::kTile, &mor, &bars[B_OUT_FULL + os], n * kNC + 32, 0, it.i, it.b);
+                };
+                while (prep < total_chunks && prep < 2 && can_prepare(prep)) { prepare(prep); ++prep; }
+                for (uint32_t c = 0; c < total_chunks; ++c) {
+                    const int k = chunk_item(c), n = c % NCH, os = c % kNOut;
+                    const Item it = item_of(k);
+                    mbar_wait(&bars[B_STAGED + os], (c / kNOut) & 1);
+                    const uint8_t *slot = smem + S::off_out + os * T::kSlot;
+                    const CUtensorMap *mo = it.col ? &moc : &mor;
+                    const int cw = it.col ? it.i : 0, ch = it.col ? 0 : it.i;
+                    tma_store_4d(mo, slot, n * kNC, cw, ch, it.b);
+                    tma_store_4d(mo, slot + T::kTile, n * kNC + 32, cw, ch, it.b);
+                    tma_store_commit();
+                    if (n == NCH - 1) {
+                        if (it.col && p.mode == MODE_FUSED) {
+                            // publish this column line: its stores (async proxy) and the stats written by the softmax group
+                            tma_store_wait_all<0>();
+                            fence_proxy_async_all();
+                            __threadfence();
+                            atomicAdd(p.done + it.b, 1u);
+                        }
+                        pub_k = k + 1;
+                    }
+                    // keep two chunks prepared ahead; slot of chunk c+2 was last used by chunk c-1, whose store must have drained
+                    while (prep < total_chunks && prep <= c + 2 && can_prepare(prep)) {
+                        tma_store_wait_read<1>();
+                        prepare(prep);
+                        ++prep;
+                    }
+                }
+                tma_store_wait_all<0>();
+            }
         }
     } else if (warp >= kWarpConv0) {
         // =============================== converters (256 threads) ===============================
@@ -327,48 +392,21 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
         reg_inc<kRegsEpi>();
         const int r = tid;
         const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
-        const bool elected = tid == 0;
         uint32_t oc = 0;
-        // make the staging slot of output chunk (k, n) ready: a row item gets its column partial by TMA, a column item
-        // only needs the slot to be free
-        auto prepare = [&](int k, int n, uint32_t c) {
-            const Item it = item_of(k);
-            const int os = c % kNOut;
-            if (it.col) { mbar_arrive(&bars[B_OUT_FULL + os]); return; }
-            if (p.mode == MODE_FUSED) { wait_done(p.done + it.b, (unsigned)p.W); fence_proxy_async_all(); }
-            uint8_t *dst = smem + S::off_out + os * T::kSlot;
-            mbar_expect_tx(&bars[B_OUT_FULL + os], T::kSlot);
-            tma_load_4d(dst, &mor, &bars[B_OUT_FULL + os], n * kNC, 0, it.i, it.b);
-            tma_load_4d(dst + T::kTile, &mor, &bars[B_OUT_FULL + os], n * kNC + 32, 0, it.i, it.b);
-        };
-        if (elected && nk > 0) prepare(0, 0, 0);
+        int dbg_n = tid == 0 ? 0 : 512;
         for (int k = 0; k < nk; ++k) {
             const Item it = item_of(k);
-            const int cw = it.col ? it.i : 0, ch = it.col ? 0 : it.i;
-            const CUtensorMap *mo = it.col ? &moc : &mor;
             float sa = 0.f, sb = 0.f;
             for (int n = 0; n < NCH; ++n, ++oc) {
                 const int os = oc % kNOut;
                 const uint32_t ob = oc % kNOB;
                 uint8_t *slot = smem + S::off_out + os * T::kSlot;
-                if (elected) {
-                    // prefetch the next chunk's slot one chunk ahead.  Across an item boundary this is only legal if the
-                    // next item does not wait for THIS item (a row line of the sample whose column line we are finishing).
-                    int k2 = k, n2 = n + 1;
-                    if (n2 == NCH) { n2 = 0; k2 = k + 1; }
-                    bool early = k2 < nk;
-                    if (early && k2 != k) {
-                        const Item nx = item_of(k2);
-                        early = !(it.col && !nx.col && nx.b == it.b && p.mode == MODE_FUSED);
-                    }
-                    if (early) {
-                        tma_store_wait_read<1>();          // slot (oc+1)%3 was last used by chunk oc-2: its store has drained
-                        prepare(k2, n2, oc + 1);
-                    }
-                }
-                mbar_wait(&bars[B_OUT_FULL + os], (oc / kNOut) & 1);
+                CCA_STAMP(4);
+                mbar_wait(&bars[B_OUT_FULL + os], (oc / kNOut) & 1);     // slot free (column item) / column partial landed (row item)
+                CCA_STAMP(4);
                 mbar_wait(&bars[B_O_FULL + ob], (oc / kNOB) & 1);
                 tc_fence_after();
+                CCA_STAMP(4);
                 if (n == 0) {
                     mbar_wait(&bars[B_SC_FULL + (k & 1)], (k >> 1) & 1);
                     const float2 sc = scale[(k & 1) * 128 + r];
@@ -379,43 +417,42 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
 #pragma unroll
                 for (int c0 = 0; c0 < kNC; c0 += 16) tmem_ld16(tl + kTmemO + ob * kNC + c0, reinterpret_cast<uint32_t *>(o + c0));
                 tmem_ld_wait();
+                CCA_STAMP(4);
                 tc_fence_before();
                 mbar_arrive(&bars[B_O_EMPTY + ob]);
-                if (r < LK) {
+                if (r < it.L) {                                          // rows >= L are clipped by the TMA store
                     uint8_t *row = slot + r * 128;
                     const int sw = r & 7;
+                    if (it.col) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {               // 16 chunks of 4 channels
-                        float4 *dst = reinterpret_cast<float4 *>(row + (j >> 3) * T::kTile + (((j & 7) ^ sw) * 16));
-                        float4 v = make_float4(o[4 * j] * sa, o[4 * j + 1] * sa, o[4 * j + 2] * sa, o[4 * j + 3] * sa);
-                        if (!it.col) {
-                            const float4 q = *dst;
-                            v.x = fmaf(q.x, sb, v.x); v.y = fmaf(q.y, sb, v.y); v.z = fmaf(q.z, sb, v.z); v.w = fmaf(q.w, sb, v.w);
+                        for (int j = 0; j < 16; ++j) {                   // 16 chunks of 4 channels
+                            float4 *dst = reinterpret_cast<float4 *>(row + (j >> 3) * T::kTile + (((j & 7) ^ sw) * 16));
+                            *dst = make_float4(o[4 * j] * sa, o[4 * j + 1] * sa, o[4 * j + 2] * sa, o[4 * j + 3] * sa);
                         }
-                        *dst = v;
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {                    // two batches of 8: all loads of a batch before its stores
+                            float4 q[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                q[j] = *reinterpret_cast<const float4 *>(row + h * T::kTile + ((j ^ sw) * 16));
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int e = 32 * h + 4 * j;
+                                float4 v;
+                                v.x = fmaf(q[j].x, sb, o[e] * sa);         v.y = fmaf(q[j].y, sb, o[e + 1] * sa);
+                                v.z = fmaf(q[j].z, sb, o[e + 2] * sa);     v.w = fmaf(q[j].w, sb, o[e + 3] * sa);
+                                *reinterpret_cast<float4 *>(row + h * T::kTile + ((j ^ sw) * 16)) = v;
+                            }
+                        }
                     }
                 }
+                CCA_STAMP(4);
                 fence_proxy_async();
-                named_bar_sync(1, 128);
-                if (elected) {
-                    tma_store_4d(mo, slot, n * kNC, cw, ch, it.b);
-                    tma_store_4d(mo, slot + T::kTile, n * kNC + 32, cw, ch, it.b);
-                    tma_store_commit();
-                }
-            }
-            if (elected && it.col && p.mode == MODE_FUSED) {
-                // publish this column line: its stores (async proxy) and the stats written by the softmax group
-                tma_store_wait_all<0>();
-                fence_proxy_async_all();
-                __threadfence();
-                atomicAdd(p.done + it.b, 1u);
-                if (k + 1 < nk) {
-                    const Item nx = item_of(k + 1);
-                    if (!nx.col && nx.b == it.b) prepare(k + 1, 0, oc);   // the deferred prefetch (all stores have drained)
-                }
+                mbar_arrive(&bars[B_STAGED + os]);                       // the store warp takes over
+                CCA_STAMP(4);
             }
         }
-        if (elected) tma_store_wait_all<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -440,7 +477,7 @@ cudaError_t launch_fwd(const void *q, const void *k, const void *v, void *out, f
     FwdParams p;
     p.B = d.B; p.H = d.H; p.W = d.W; p.C = d.C; p.Cq = d.Cq;
     p.mode = mode; p.stats = stats; p.lse = lse; p.done = done;
-    p.dbg = g_dbg ? g_dbg + (mode == MODE_ROW_ONLY ? 2048 : 0) : nullptr;
+    p.dbg = g_dbg ? g_dbg + (mode == MODE_ROW_ONLY ? 2560 : 0) : nullptr;
     auto kern = cca_tc_fwd_kernel<LK>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem<LK>::kBytes);
     if (e != cudaSuccess) return e;

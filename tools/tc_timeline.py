@@ -11,19 +11,34 @@ k = torch.randn(B, Cq, H, W, device=dev).contiguous(memory_format=torch.channels
 v = torch.randn(B, C, H, W, device=dev).contiguous(memory_format=torch.channels_last)
 for _ in range(3):
     cca_forward(q, k, v, impl="tc")
-buf = torch.zeros(2 * 4 * 512, dtype=torch.int64, device=dev)
+buf = torch.zeros(2 * 5 * 512, dtype=torch.int64, device=dev)
 fn = lib.cca_b200__set_debug_buffer
 fn.argtypes = [ctypes.c_void_p]; fn.restype = None
 fn(buf.data_ptr())
 cca_forward(q, k, v, impl="tc")
 torch.cuda.synchronize()
 fn(None)
-t = buf.cpu().view(2, 4, 512)
-names = ["producer(slot free->issue)", "converter(full, op_empty, done)", "mma", "softmax/epilogue"]
-for ps, pname in enumerate(["COLUMN pass", "ROW pass"]):
-    base = min(int(x) for x in t[ps].flatten() if x > 0)
+import time
+def timeit(tag):
+    for _ in range(3): cca_forward(q, k, v, impl="tc")
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20): cca_forward(q, k, v, impl="tc")
+    e1.record(); torch.cuda.synchronize()
+    print(tag, "fwd ms", e0.elapsed_time(e1) / 20)
+timeit("fused launch  :")
+tp = lib.cca_b200__set_two_pass; tp.argtypes = [ctypes.c_int]; tp.restype = None
+tp(1); timeit("two launches  :"); tp(0)
+t = buf.cpu().view(2, 5, 512)
+names = ["producer(slot free->issue)", "converter(full, op_empty, done)", "mma", "softmax", "epilogue(top, out_full, o_full, tmem_ld done, sts done, staged)"]
+for ps, pname in enumerate(["FUSED / COLUMN pass", "ROW pass"]):
+    vals = [int(x) for x in t[ps].flatten() if x > 0]
+    if not vals:
+        continue
+    base = min(vals)
     print("=====", pname)
-    for role in range(4):
+    for role in range(5):
         st = [int(x) - base for x in t[ps, role] if x > 0]
         print(f"--- {names[role]}: {len(st)} stamps")
         print(" ".join(str(x) for x in st[:70]))
