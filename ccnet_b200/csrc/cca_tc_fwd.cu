@@ -31,8 +31,8 @@ namespace cca {
 namespace {
 using namespace tc;
 
-constexpr int kTmemCols = 512;      // S [0,128)   P hi/lo [128,256)   O ring 4 x 64 [256,512)
-constexpr int kTmemP = 128, kTmemO = 256, kNOB = 4;
+constexpr int kTmemCols = 512;      // S [0,128)   P double buffer (hi/lo) [128,256) [256,384)   O ring 2 x 64 [384,512)
+constexpr int kTmemP = 128, kTmemO = 384, kNOB = 2;
 constexpr int kRegsSoft = 168, kRegsEpi = 128;
 static_assert(reg_pool_ok(kRegsSoft, kRegsEpi), "setmaxnreg pool");
 constexpr int kNLd = 3, kNOut = 3;  // ring depths (smem slots)
@@ -97,7 +97,7 @@ template <int LK> struct FwdSmem {
 };
 
 enum { B_LD_FULL = 0, B_LD_EMPTY = 3, B_OP_FULL = 6, B_OP_EMPTY = 8, B_S_FULL = 10, B_S_EMPTY = 11, B_P_FULL = 12,
-       B_P_EMPTY = 13, B_O_FULL = 14, B_O_EMPTY = 18, B_OUT_FULL = 22, B_SC_EMPTY = 25, B_SC_FULL = 27, B_STAGED = 29, B_COUNT = 32 };
+       B_P_EMPTY = 14, B_O_FULL = 16, B_O_EMPTY = 18, B_OUT_FULL = 20, B_SC_EMPTY = 23, B_SC_FULL = 25, B_STAGED = 27, B_COUNT = 30 };
 
 __device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p)
 {
@@ -133,6 +133,9 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
     const int KQ = p.Cq / 16;                 // k-steps of the S MMA
     const int n_items = total_items(p);
     const int nk = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items of this CTA
+    // ring order:  Q0 K0 | V0[0..qkpos) Q1 K1 V0[qkpos..NCH) | V1[0..qkpos) Q2 K2 ...   (Q,K of the next item are slipped in
+    // after the first chunks of the current one, so neither S(k+1) nor the first P V chunk of an item waits for the other)
+    const int qkpos = NCH >= 3 ? 2 : NCH - 1;
 
     if (tid == 0) {
         for (int i = 0; i < kNLd; ++i) { mbar_init(&bars[B_LD_FULL + i], 1); mbar_init(&bars[B_LD_EMPTY + i], kConvThreads); }
@@ -141,7 +144,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
         for (int i = 0; i < kNOut; ++i) { mbar_init(&bars[B_OUT_FULL + i], 1); mbar_init(&bars[B_STAGED + i], 128); }
         for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_SC_EMPTY + i], 128); mbar_init(&bars[B_SC_FULL + i], 128); }
         mbar_init(&bars[B_S_FULL], 1); mbar_init(&bars[B_S_EMPTY], 128);
-        mbar_init(&bars[B_P_FULL], 128); mbar_init(&bars[B_P_EMPTY], 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_P_FULL + i], 128); mbar_init(&bars[B_P_EMPTY + i], 1); }
         fence_mbar_init();
         prefetch_tmap(&mqc); prefetch_tmap(&mqr); prefetch_tmap(&mkc); prefetch_tmap(&mkr);
         prefetch_tmap(&mvc); prefetch_tmap(&mvr); prefetch_tmap(&moc); prefetch_tmap(&mor);
@@ -178,8 +181,10 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                 emit(&mkc, &mkr, 0, cur);
                 for (int k = 0; k < nk; ++k) {
                     Item nxt = cur;
-                    if (k + 1 < nk) { nxt = item_of(k + 1); emit(&mqc, &mqr, 0, nxt); emit(&mkc, &mkr, 0, nxt); }
-                    for (int n = 0; n < NCH; ++n) emit(&mvc, &mvr, n * kNC, cur);
+                    for (int n = 0; n < NCH; ++n) {
+                        if (n == qkpos && k + 1 < nk) { nxt = item_of(k + 1); emit(&mqc, &mqr, 0, nxt); emit(&mkc, &mkr, 0, nxt); }
+                        emit(&mvc, &mvr, n * kNC, cur);
+                    }
                     cur = nxt;
                 }
             }
@@ -210,12 +215,13 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             };
             issue_s(0);
             for (int k = 0; k < nk; ++k) {
-                if (k + 1 < nk) issue_s(k + 1);
                 CCA_STAMP(2);
-                mbar_wait(&bars[B_P_FULL], k & 1);
+                mbar_wait(&bars[B_P_FULL + (k & 1)], (k >> 1) & 1);
                 tc_fence_after();
                 CCA_STAMP(2);
+                const uint32_t pbuf = tmem + kTmemP + (k & 1) * 128;
                 for (int n = 0; n < NCH; ++n, ++u, ++oc) {
+                    if (n == qkpos && k + 1 < nk) issue_s(k + 1);
                     const uint32_t vb = op_base + (u & 1) * T::kOp;
                     const uint32_t ob = oc % kNOB;
                     mbar_wait(&bars[B_OP_FULL + (u & 1)], (u >> 1) & 1);
@@ -226,7 +232,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                         const uint32_t d = tmem + kTmemO + ob * kNC;
 #pragma unroll
                         for (int ks = 0; ks < LK / 16; ++ks) {
-                            const uint32_t ph = tmem + kTmemP + ks * 8, pl = ph + LK / 2;
+                            const uint32_t ph = pbuf + ks * 8, pl = ph + LK / 2;
                             const uint64_t vh = smem_desc(vb + ks * 256, 128, T::kPlane);
                             const uint64_t vl = smem_desc(vb + 8 * T::kPlane + ks * 256, 128, T::kPlane);
                             mma_f16_ts(d, ph, vh, idesc_o, ks > 0);
@@ -239,7 +245,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                     commit_to(&bars[B_OP_EMPTY + (u & 1)]);
                     CCA_STAMP(2);
                 }
-                commit_to(&bars[B_P_EMPTY]);
+                commit_to(&bars[B_P_EMPTY + (k & 1)]);
             }
         } else if (warp == kWarpStore) {
             // =============================== store warp (one lane): staging slots <-> global ===============================
@@ -372,19 +378,20 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             mbar_arrive(&bars[B_SC_FULL + (k & 1)]);          // release: scales and the stats / lse written above
             // ---------------- P -> TMEM as packed bf16 pairs: hi at [kTmemP, +LK/2), lo at [kTmemP+LK/2, +LK/2)
             CCA_STAMP(3);
-            mbar_wait(&bars[B_P_EMPTY], (k & 1) ^ 1);
+            mbar_wait(&bars[B_P_EMPTY + (k & 1)], ((k >> 1) & 1) ^ 1);    // P V of item k-2 has finished reading this buffer
             tc_fence_after();
+            const uint32_t pdst = tl + kTmemP + (k & 1) * 128;
 #pragma unroll
             for (int c0 = 0; c0 < LK / 2; c0 += 8) {
                 uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) split2(s[2 * (c0 + e)], s[2 * (c0 + e) + 1], hi[e], lo[e]);
-                tmem_st8(tl + kTmemP + c0, hi);
-                tmem_st8(tl + kTmemP + LK / 2 + c0, lo);
+                tmem_st8(pdst + c0, hi);
+                tmem_st8(pdst + LK / 2 + c0, lo);
             }
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&bars[B_P_FULL]);
+            mbar_arrive(&bars[B_P_FULL + (k & 1)]);
             CCA_STAMP(3);
         }
     } else {
