@@ -44,6 +44,7 @@ int cca_b200_version(void) { return CCA_B200_VERSION; }
 CCA_API void cca_b200__set_debug_buffer(void *p) { set_tc_debug_buffer(p); }
 // A/B aid: run the tensor-core forward as two launches (column pass, row pass) instead of the fused launch
 CCA_API void cca_b200__set_two_pass(int on) { set_tc_two_pass(on); }
+CCA_API void cca_b200__set_bwd_debug_buffer(void *p) { set_tc_bwd_debug_buffer(p); }
 const char *cca_b200_last_error(void) { return g_err; }
 const char *cca_b200_strerror(int s)
 {

@@ -50,5 +50,6 @@ cudaError_t tc_backward(const void *dout, const void *q, const void *k, const vo
 void count_launch(int n = 1);
 void set_tc_debug_buffer(void *p);
 void set_tc_two_pass(int on);
+void set_tc_bwd_debug_buffer(void *p);
 
 }  // namespace cca

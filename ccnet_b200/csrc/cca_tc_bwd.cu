@@ -32,22 +32,36 @@ struct BwdParams {
     int L, NL, col;
     const float *lse;
     const float *delta;
+    long long *dbg;
 };
+
+#define CCA_STAMP(role)                                                                          \
+    do {                                                                                         \
+        if (p.dbg && blockIdx.x == 0 && dbg_n < 512) p.dbg[(role) * 512 + dbg_n++] = clock64();  \
+    } while (0)
+
+constexpr int kNOp = 3;             // rotating operand buffers
 
 template <int LK> struct BwdSmem {
     using T = Tiles<LK>;
     static constexpr int off_ld = 0;                       // 2 load slots
-    static constexpr int off_out = off_ld + 2 * T::kSlot;  // 2 out slots
-    static constexpr int off_p = off_out + 2 * T::kSlot;   // P / dS planes (hi, lo); over-reads land in op buffers
-    static constexpr int off_op = off_p + T::kP;           // 2 operand buffers
-    static constexpr int off_tail = off_op + 2 * T::kOp;   // 256 B pad for the 16-row over-read of M=128 MMAs
+    static constexpr int off_out = off_ld + 2 * T::kSlot;  // 1 out slot (the epilogue has slack; the store warp drives it)
+    static constexpr int off_p = off_out + T::kSlot;       // P / dS planes (hi, lo); over-reads land in the operand buffers
+    static constexpr int off_op = off_p + T::kP;           // kNOp operand buffers
+    static constexpr int off_tail = off_op + kNOp * T::kOp;// 256 B pad for the 16-row over-read of M=128 MMAs
     static constexpr int off_bar = off_tail + 256;
-    static constexpr int kBytes = off_bar + 256 + 1024;
+    static constexpr int kBytes = off_bar + 320;
+    static_assert(kBytes <= 232448, "shared memory budget");
 };
 
-enum { B_LD_FULL = 0, B_LD_EMPTY = 2, B_OP_FULL = 4, B_OP_EMPTY = 6, B_S_FULL = 8, B_S_EMPTY = 9, B_P_FULL = 10,
-       B_P_EMPTY = 11, B_O_FULL = 12, B_O_EMPTY = 14, B_OUT_FULL = 16, B_DP_FULL = 18, B_DS_FULL = 19, B_COUNT = 20 };
+enum { B_LD_FULL = 0, B_LD_EMPTY = 2, B_OP_FULL = 4, B_OP_EMPTY = 7, B_S_FULL = 10, B_S_EMPTY = 11, B_P_FULL = 12,
+       B_P_EMPTY = 13, B_O_FULL = 14, B_O_EMPTY = 16, B_OUT_FULL = 18, B_STAGED = 19, B_DP_FULL = 20, B_DS_FULL = 21,
+       B_COUNT = 22 };
 
+// Per line the ring carries  Q K (V_n dO_n)* Q K ; item g is converted into operand buffer g % 3, so the conversion of
+// the next chunk overlaps the MMAs of the current one.  MMAs per line: S (phase A), per chunk dP += dO V^T then
+// dV = P^T dO (phase B; the V buffer is released right after the dP MMAs), dS by the P/dS group (phase C),
+// dQ = dS K and dK = dS^T Q (phase D).
 template <int LK>
 __global__ void __launch_bounds__(kThreads, 1)
 cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
@@ -57,8 +71,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
 {
     using T = Tiles<LK>;
     using S = BwdSmem<LK>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S::off_bar);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::off_bar + 8 * B_COUNT);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -67,14 +80,15 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
     const int NI = 4 + 2 * NCH;               // load items per line: Q K (V dO)* Q K
     const int NO = NCH + 2;                   // output items per line: dV chunks, dQ, dK
     const int total_lines = p.B * p.NL;
+    const int nk = (total_lines - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars[B_LD_FULL + i], 1);            mbar_init(&bars[B_LD_EMPTY + i], kConvThreads);
-            mbar_init(&bars[B_OP_FULL + i], kConvThreads); mbar_init(&bars[B_OP_EMPTY + i], 1);
             mbar_init(&bars[B_O_FULL + i], 1);             mbar_init(&bars[B_O_EMPTY + i], 128);
-            mbar_init(&bars[B_OUT_FULL + i], 1);
         }
+        for (int i = 0; i < kNOp; ++i) { mbar_init(&bars[B_OP_FULL + i], kConvThreads); mbar_init(&bars[B_OP_EMPTY + i], 1); }
+        mbar_init(&bars[B_OUT_FULL], 1); mbar_init(&bars[B_STAGED], 128);
         mbar_init(&bars[B_S_FULL], 1);   mbar_init(&bars[B_S_EMPTY], 128);
         mbar_init(&bars[B_P_FULL], 128); mbar_init(&bars[B_P_EMPTY], 1);
         mbar_init(&bars[B_DP_FULL], 1);  mbar_init(&bars[B_DS_FULL], 128);
@@ -88,149 +102,167 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
+    auto line_of = [&](int k) { return (int)blockIdx.x + k * (int)gridDim.x; };
     auto line_coords = [&](int line, int &cw, int &ch, int &cb) {
         cb = line / p.NL;
         const int i = line - cb * p.NL;
         if (p.col) { cw = i; ch = 0; } else { cw = 0; ch = i; }
     };
+    // output item i of a line: i < NCH -> dV chunk i; NCH -> dQ; NCH+1 -> dK
+    auto out_map = [&](int i) -> const CUtensorMap * { return i < NCH ? &mdv : (i == NCH ? &mdq : &mdk); };
+    auto out_c0 = [&](int i) { return i < NCH ? i * kNC : 0; };
 
-    if (warp >= kWarpProducer) reg_dec<kRegsMisc>();
-    else if (warp >= kWarpConv0) reg_dec<kRegsConv>();
-    if (warp > kWarpMma) {
-        // idle padding warps
-    } else if (warp == kWarpProducer) {
-        // =============================== TMA producer ===============================
-        if (lane == 0) {
-            uint32_t g = 0;
-            for (int line = blockIdx.x; line < total_lines; line += gridDim.x) {
-                int cw, ch, cb;
-                line_coords(line, cw, ch, cb);
-                for (int item = 0; item < NI; ++item, ++g) {
-                    const int slot = g & 1;
-                    mbar_wait(&bars[B_LD_EMPTY + slot], ((g >> 1) & 1) ^ 1);
-                    uint8_t *dst = smem + S::off_ld + slot * T::kSlot;
-                    mbar_expect_tx(&bars[B_LD_FULL + slot], T::kSlot);
-                    const CUtensorMap *m;
-                    int c0 = 0;
-                    if (item < 2 || item >= 2 + 2 * NCH) m = (item & 1) ? &mk : &mq;
-                    else { m = (item & 1) ? &mdo : &mv; c0 = ((item - 2) >> 1) * kNC; }
-                    tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, cb);
-                    tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, cb);
+    if (warp >= kWarpProducer) {
+        reg_dec<kRegsMisc>();
+        if (warp == kWarpProducer) {
+            // =============================== TMA producer ===============================
+            if (lane == 0) {
+                uint32_t g = 0;
+                int dbg_n = 0;
+                for (int k = 0; k < nk; ++k) {
+                    int cw, ch, cb;
+                    line_coords(line_of(k), cw, ch, cb);
+                    for (int item = 0; item < NI; ++item, ++g) {
+                        const int slot = g & 1;
+                        mbar_wait(&bars[B_LD_EMPTY + slot], ((g >> 1) & 1) ^ 1);
+                        CCA_STAMP(0);
+                        uint8_t *dst = smem + S::off_ld + slot * T::kSlot;
+                        mbar_expect_tx(&bars[B_LD_FULL + slot], T::kSlot);
+                        const CUtensorMap *m;
+                        int c0 = 0;
+                        if (item < 2 || item >= 2 + 2 * NCH) m = (item & 1) ? &mk : &mq;
+                        else { m = (item & 1) ? &mdo : &mv; c0 = ((item - 2) >> 1) * kNC; }
+                        tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, cb);
+                        tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, cb);
+                    }
                 }
             }
-        }
-    } else if (warp == kWarpMma) {
-        // =============================== MMA issuer ===============================
-        const uint32_t id_kk_s = instr_desc(kFmtBF16, kFmtBF16, 128, LK, false, false);    // S, dP : K-major x K-major, N = LK
-        const uint32_t id_mn_mn = instr_desc(kFmtBF16, kFmtBF16, 128, kNC, true, true);    // dV, dK: A^T planes x channel planes
-        const uint32_t id_k_mn = instr_desc(kFmtBF16, kFmtBF16, 128, kNC, false, true);    // dQ
-        const uint32_t op0 = smem_u32(smem + S::off_op), op1 = op0 + T::kOp, pb = smem_u32(smem + S::off_p);
-        const uint32_t LO8 = 8 * T::kPlane, LOP = T::kPP * T::kPlane;
-        uint32_t u = 0, oc = 0, ln = 0;
-        for (int line = blockIdx.x; line < total_lines; line += gridDim.x, ++ln) {
-            // ---- phase A: S = Q K^T   (Q in op0, K in op1)
-            mbar_wait(&bars[B_OP_FULL + 0], (u >> 1) & 1);
-            mbar_wait(&bars[B_OP_FULL + 1], (u >> 1) & 1);
-            mbar_wait(&bars[B_S_EMPTY], (ln & 1) ^ 1);
-            tc_fence_after();
-            for (int ks = 0; ks < KQ; ++ks) {
-                const uint32_t ao = ks * 2 * T::kPlane;
-                mma_split3(tmem, smem_desc(op0 + ao, T::kPlane, 128), smem_desc(op0 + LO8 + ao, T::kPlane, 128),
-                           smem_desc(op1 + ao, T::kPlane, 128), smem_desc(op1 + LO8 + ao, T::kPlane, 128), id_kk_s, ks > 0);
-            }
-            commit_to(&bars[B_S_FULL]);
-            commit_to(&bars[B_OP_EMPTY + 0]);
-            commit_to(&bars[B_OP_EMPTY + 1]);
-            u += 2;
-            mbar_wait(&bars[B_P_FULL], ln & 1);
-            // ---- phase B: per chunk  dP += dO V^T  and  dV = P^T dO      (V in op0, dO in op1)
-            for (int n = 0; n < NCH; ++n, u += 2, ++oc) {
-                mbar_wait(&bars[B_OP_FULL + 0], (u >> 1) & 1);
-                mbar_wait(&bars[B_OP_FULL + 1], (u >> 1) & 1);
-                tc_fence_after();
-#pragma unroll
-                for (int ks = 0; ks < kNC / 16; ++ks) {
-                    const uint32_t ao = ks * 2 * T::kPlane;
-                    mma_split3(tmem, smem_desc(op1 + ao, T::kPlane, 128), smem_desc(op1 + LO8 + ao, T::kPlane, 128),
-                               smem_desc(op0 + ao, T::kPlane, 128), smem_desc(op0 + LO8 + ao, T::kPlane, 128),
-                               id_kk_s, n > 0 || ks > 0);
+        } else if (warp == kWarpMma) {
+            // =============================== MMA issuer ===============================
+            const uint32_t id_kk_s = instr_desc(kFmtBF16, kFmtBF16, 128, LK, false, false);    // S, dP : K-major x K-major, N = LK
+            const uint32_t id_mn_mn = instr_desc(kFmtBF16, kFmtBF16, 128, kNC, true, true);    // dV, dK: A^T planes x channel planes
+            const uint32_t id_k_mn = instr_desc(kFmtBF16, kFmtBF16, 128, kNC, false, true);    // dQ
+            const uint32_t op_base = smem_u32(smem + S::off_op), pb = smem_u32(smem + S::off_p);
+            const uint32_t LO8 = 8 * T::kPlane, LOP = T::kPP * T::kPlane;
+            uint32_t u = 0, oc = 0;
+            int dbg_n = lane == 0 ? 0 : 512;
+            auto opb = [&](uint32_t g) { return op_base + (g % kNOp) * T::kOp; };
+            auto wait_op = [&](uint32_t g) { mbar_wait(&bars[B_OP_FULL + g % kNOp], (g / kNOp) & 1); };
+            auto free_op = [&](uint32_t g) { commit_to(&bars[B_OP_EMPTY + g % kNOp]); };
+            for (int k = 0; k < nk; ++k) {
+                CCA_STAMP(2);
+                // ---- phase A: S = Q K^T
+                {
+                    const uint32_t q = opb(u), kk = opb(u + 1);
+                    wait_op(u); wait_op(u + 1);
+                    mbar_wait(&bars[B_S_EMPTY], (k & 1) ^ 1);
+                    tc_fence_after();
+                    for (int ks = 0; ks < KQ; ++ks) {
+                        const uint32_t ao = ks * 2 * T::kPlane;
+                        mma_split3(tmem, smem_desc(q + ao, T::kPlane, 128), smem_desc(q + LO8 + ao, T::kPlane, 128),
+                                   smem_desc(kk + ao, T::kPlane, 128), smem_desc(kk + LO8 + ao, T::kPlane, 128), id_kk_s, ks > 0);
+                    }
+                    commit_to(&bars[B_S_FULL]);
+                    free_op(u); free_op(u + 1);
+                    u += 2;
                 }
-                mbar_wait(&bars[B_O_EMPTY + (oc & 1)], ((oc >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d = tmem + 128 + (oc & 1) * kNC;
-#pragma unroll
-                for (int ks = 0; ks < LK / 16; ++ks) {
-                    const uint32_t ko = ks * 256;     // 16 query pixels = 16 rows x 16 B inside every plane
-                    mma_split3(d, smem_desc(pb + ko, 128, T::kPlane), smem_desc(pb + LOP + ko, 128, T::kPlane),
-                               smem_desc(op1 + ko, 128, T::kPlane), smem_desc(op1 + LO8 + ko, 128, T::kPlane),
-                               id_mn_mn, ks > 0);
+                CCA_STAMP(2);
+                mbar_wait(&bars[B_P_FULL], k & 1);
+                CCA_STAMP(2);
+                // ---- phase B: per chunk  dP += dO V^T  and  dV = P^T dO
+                for (int n = 0; n < NCH; ++n, u += 2, ++oc) {
+                    const uint32_t vb = opb(u), db = opb(u + 1);
+                    wait_op(u); wait_op(u + 1);
+                    tc_fence_after();
+                    mma_split3_loop<kNC / 16>(tmem, db, db + LO8, 2 * T::kPlane, T::kPlane, 128,
+                                              vb, vb + LO8, 2 * T::kPlane, T::kPlane, 128, id_kk_s, n > 0);
+                    free_op(u);                                   // V is only needed by dP
+                    mbar_wait(&bars[B_O_EMPTY + (oc & 1)], ((oc >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    mma_split3_loop<LK / 16>(tmem + 128 + (oc & 1) * kNC, pb, pb + LOP, 256, 128, T::kPlane,
+                                             db, db + LO8, 256, 128, T::kPlane, id_mn_mn, false);
+                    commit_to(&bars[B_O_FULL + (oc & 1)]);
+                    free_op(u + 1);
+                    CCA_STAMP(2);
                 }
-                commit_to(&bars[B_O_FULL + (oc & 1)]);
-                commit_to(&bars[B_OP_EMPTY + 0]);
-                commit_to(&bars[B_OP_EMPTY + 1]);
-            }
-            commit_to(&bars[B_DP_FULL]);
-            // ---- phase D: dQ = dS K,  dK = dS^T Q      (Q in op0, K in op1, dS in the P planes)
-            mbar_wait(&bars[B_DS_FULL], ln & 1);
-            mbar_wait(&bars[B_OP_FULL + 0], (u >> 1) & 1);
-            mbar_wait(&bars[B_OP_FULL + 1], (u >> 1) & 1);
-            mbar_wait(&bars[B_O_EMPTY + (oc & 1)], ((oc >> 1) & 1) ^ 1);
-            tc_fence_after();
-            {
-                const uint32_t d = tmem + 128 + (oc & 1) * kNC;
-#pragma unroll
-                for (int ks = 0; ks < LK / 16; ++ks) {
-                    const uint32_t ao = ks * 2 * T::kPlane, ko = ks * 256;
-                    mma_split3(d, smem_desc(pb + ao, T::kPlane, 128), smem_desc(pb + LOP + ao, T::kPlane, 128),
-                               smem_desc(op1 + ko, 128, T::kPlane), smem_desc(op1 + LO8 + ko, 128, T::kPlane),
-                               id_k_mn, ks > 0);
+                commit_to(&bars[B_DP_FULL]);
+                // ---- phase D: dQ = dS K,  dK = dS^T Q      (dS in the P planes)
+                mbar_wait(&bars[B_DS_FULL], k & 1);
+                CCA_STAMP(2);
+                {
+                    const uint32_t q = opb(u), kk = opb(u + 1);
+                    wait_op(u); wait_op(u + 1);
+                    mbar_wait(&bars[B_O_EMPTY + (oc & 1)], ((oc >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    mma_split3_loop<LK / 16>(tmem + 128 + (oc & 1) * kNC, pb, pb + LOP, 2 * T::kPlane, T::kPlane, 128,
+                                             kk, kk + LO8, 256, 128, T::kPlane, id_k_mn, false);
+                    commit_to(&bars[B_O_FULL + (oc & 1)]);
+                    free_op(u + 1);
+                    ++oc;
+                    mbar_wait(&bars[B_O_EMPTY + (oc & 1)], ((oc >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    mma_split3_loop<LK / 16>(tmem + 128 + (oc & 1) * kNC, pb, pb + LOP, 256, 128, T::kPlane,
+                                             q, q + LO8, 256, 128, T::kPlane, id_mn_mn, false);
+                    commit_to(&bars[B_O_FULL + (oc & 1)]);
+                    free_op(u);
+                    ++oc;
+                    commit_to(&bars[B_P_EMPTY]);
+                    u += 2;
                 }
-                commit_to(&bars[B_O_FULL + (oc & 1)]);
-                ++oc;
+                CCA_STAMP(2);
             }
-            mbar_wait(&bars[B_O_EMPTY + (oc & 1)], ((oc >> 1) & 1) ^ 1);
-            tc_fence_after();
-            {
-                const uint32_t d = tmem + 128 + (oc & 1) * kNC;
-#pragma unroll
-                for (int ks = 0; ks < LK / 16; ++ks) {
-                    const uint32_t ko = ks * 256;
-                    mma_split3(d, smem_desc(pb + ko, 128, T::kPlane), smem_desc(pb + LOP + ko, 128, T::kPlane),
-                               smem_desc(op0 + ko, 128, T::kPlane), smem_desc(op0 + LO8 + ko, 128, T::kPlane),
-                               id_mn_mn, ks > 0);
+        } else if (warp == kWarpStore) {
+            // =============================== store warp (one lane): the output staging slot <-> global ===============================
+            if (lane == 0) {
+                const uint32_t total = (uint32_t)nk * NO;
+                uint8_t *slot = smem + S::off_out;
+                for (uint32_t c = 0; c < total; ++c) {
+                    const int k = c / NO, i = c - k * NO;
+                    int cw, ch, cb;
+                    line_coords(line_of(k), cw, ch, cb);
+                    // slot is free once the previous store has been read out of shared memory
+                    tma_store_wait_read<0>();
+                    if (p.col) mbar_arrive(&bars[B_OUT_FULL]);
+                    else {                                         // row pass: fetch the column-pass partial to accumulate onto
+                        mbar_expect_tx(&bars[B_OUT_FULL], T::kSlot);
+                        tma_load_4d(slot, out_map(i), &bars[B_OUT_FULL], out_c0(i), cw, ch, cb);
+                        tma_load_4d(slot + T::kTile, out_map(i), &bars[B_OUT_FULL], out_c0(i) + 32, cw, ch, cb);
+                    }
+                    mbar_wait(&bars[B_STAGED], c & 1);
+                    tma_store_4d(out_map(i), slot, out_c0(i), cw, ch, cb);
+                    tma_store_4d(out_map(i), slot + T::kTile, out_c0(i) + 32, cw, ch, cb);
+                    tma_store_commit();
                 }
-                commit_to(&bars[B_O_FULL + (oc & 1)]);
-                ++oc;
+                tma_store_wait_all<0>();
             }
-            commit_to(&bars[B_OP_EMPTY + 0]);
-            commit_to(&bars[B_OP_EMPTY + 1]);
-            commit_to(&bars[B_P_EMPTY]);
-            u += 2;
         }
     } else if (warp >= kWarpConv0) {
         // =============================== converters (256 threads) ===============================
+        reg_dec<kRegsConv>();
         const int t = tid - kWarpConv0 * 32;
-        uint32_t g = 0;
-        for (int line = blockIdx.x; line < total_lines; line += gridDim.x) {
-            for (int item = 0; item < NI; ++item, ++g) {
-                const int slot = g & 1, ob = g & 1;
-                mbar_wait(&bars[B_LD_FULL + slot], (g >> 1) & 1);
-                mbar_wait(&bars[B_OP_EMPTY + ob], ((g >> 1) & 1) ^ 1);
-                convert_slot<LK>(smem + S::off_ld + slot * T::kSlot, smem + S::off_op + ob * T::kOp, t);
-                fence_proxy_async();
-                mbar_arrive(&bars[B_OP_FULL + ob]);
-                mbar_arrive(&bars[B_LD_EMPTY + slot]);
-            }
+        const uint32_t total = (uint32_t)nk * NI;
+        int dbg_n = t == 0 ? 0 : 512;
+        for (uint32_t g = 0; g < total; ++g) {
+            const int slot = g & 1, ob = g % kNOp;
+            mbar_wait(&bars[B_LD_FULL + slot], (g >> 1) & 1);
+            CCA_STAMP(1);
+            mbar_wait(&bars[B_OP_EMPTY + ob], ((g / kNOp) & 1) ^ 1);
+            CCA_STAMP(1);
+            convert_slot<LK>(smem + S::off_ld + slot * T::kSlot, smem + S::off_op + ob * T::kOp, t);
+            fence_proxy_async();
+            mbar_arrive(&bars[B_OP_FULL + ob]);
+            mbar_arrive(&bars[B_LD_EMPTY + slot]);
+            CCA_STAMP(1);
         }
     } else if (warp >= 4) {
         // =============================== P / dS group (128 threads, TMEM lane == query pixel) ===============================
         reg_inc<kRegsSoft>();
         const int r = tid - 128;
         const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        uint32_t ln = 0;
-        for (int line = blockIdx.x; line < total_lines; line += gridDim.x, ++ln) {
+        int dbg_n = r == 0 ? 0 : 512;
+        for (int k = 0; k < nk; ++k) {
             int cw, ch, cb;
-            line_coords(line, cw, ch, cb);
+            line_coords(line_of(k), cw, ch, cb);
             const bool rvalid = r < p.L;
             float lse2 = 0.f, dl = 0.f;
             if (rvalid) {
@@ -240,8 +272,10 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
             }
             uint8_t *ph = smem + S::off_p + r * 16, *pl = ph + T::kPP * T::kPlane;
             // ---------------- P = exp(S - lse)
-            mbar_wait(&bars[B_S_FULL], ln & 1);
+            CCA_STAMP(3);
+            mbar_wait(&bars[B_S_FULL], k & 1);
             tc_fence_after();
+            CCA_STAMP(3);
             {
                 float s[LK];
 #pragma unroll
@@ -253,7 +287,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                     const bool ok = rvalid && j < p.L && !(p.col && j == r);
                     s[j] = ok ? exp2f(s[j] * kLog2e - lse2) : 0.f;
                 }
-                mbar_wait(&bars[B_P_EMPTY], (ln & 1) ^ 1);
+                mbar_wait(&bars[B_P_EMPTY], (k & 1) ^ 1);
                 if (r < LK) {
 #pragma unroll
                     for (int kc = 0; kc < T::kPP; ++kc) {
@@ -265,10 +299,12 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                 }
                 fence_proxy_async();
                 mbar_arrive(&bars[B_P_FULL]);
+                CCA_STAMP(3);
             }
             // ---------------- dS = P * (dP - delta)   (all MMAs that read P have completed: DP_FULL is committed after them)
-            mbar_wait(&bars[B_DP_FULL], ln & 1);
+            mbar_wait(&bars[B_DP_FULL], k & 1);
             tc_fence_after();
+            CCA_STAMP(3);
             {
                 float dp[LK];
 #pragma unroll
@@ -297,6 +333,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                 }
                 fence_proxy_async();
                 mbar_arrive(&bars[B_DS_FULL]);
+                CCA_STAMP(3);
             }
         }
     } else {
@@ -304,74 +341,52 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
         reg_inc<kRegsEpi>();
         const int r = tid;
         const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
-        const bool elected = tid == 0;
+        uint8_t *slot = smem + S::off_out;
         uint32_t oc = 0;
-        // output item i of a line: i < NCH -> dV chunk i; NCH -> dQ; NCH+1 -> dK
-        auto out_map = [&](int i) -> const CUtensorMap * { return i < NCH ? &mdv : (i == NCH ? &mdq : &mdk); };
-        auto out_c0 = [&](int i) { return i < NCH ? i * kNC : 0; };
-        if (!p.col && elected) {                             // prefetch the partial of the very first output item
-            int cw, ch, cb;
-            line_coords(blockIdx.x, cw, ch, cb);
-            uint8_t *dst = smem + S::off_out;
-            mbar_expect_tx(&bars[B_OUT_FULL + 0], T::kSlot);
-            tma_load_4d(dst, out_map(0), &bars[B_OUT_FULL + 0], 0, cw, ch, cb);
-            tma_load_4d(dst + T::kTile, out_map(0), &bars[B_OUT_FULL + 0], 32, cw, ch, cb);
-        }
-        for (int line = blockIdx.x; line < total_lines; line += gridDim.x) {
-            int cw, ch, cb;
-            line_coords(line, cw, ch, cb);
+        int dbg_n = tid == 0 ? 0 : 512;
+        for (int k = 0; k < nk; ++k) {
             for (int i = 0; i < NO; ++i, ++oc) {
-                // one output item: TMEM accumulator -> (+ partial) -> swizzled staging -> TMA store
-                const int os = oc & 1;
-                uint8_t *slot = smem + S::off_out + os * T::kSlot;
-                if (elected) {
+                const int ob = oc & 1;
+                CCA_STAMP(4);
+                mbar_wait(&bars[B_OUT_FULL], oc & 1);                 // staging slot free / column partial landed
+                mbar_wait(&bars[B_O_FULL + ob], (oc >> 1) & 1);
+                tc_fence_after();
+                CCA_STAMP(4);
+                float o[kNC];
+#pragma unroll
+                for (int c0 = 0; c0 < kNC; c0 += 16) tmem_ld16(tl + 128 + ob * kNC + c0, reinterpret_cast<uint32_t *>(o + c0));
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&bars[B_O_EMPTY + ob]);
+                if (r < p.L) {                                        // rows >= L are clipped by the TMA store
+                    uint8_t *row = slot + r * 128;
+                    const int sw = r & 7;
                     if (p.col) {
-                        tma_store_wait_read<1>();
-                        mbar_arrive(&bars[B_OUT_FULL + os]);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            *reinterpret_cast<float4 *>(row + (j >> 3) * T::kTile + (((j & 7) ^ sw) * 16)) =
+                                make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
                     } else {
-                        tma_store_wait_read<0>();
-                        int nline = line, ni = i + 1;
-                        if (ni == NO) { ni = 0; nline = line + gridDim.x; }
-                        if (nline < total_lines) {
-                            int w2, h2, b2;
-                            line_coords(nline, w2, h2, b2);
-                            uint8_t *dst = smem + S::off_out + (os ^ 1) * T::kSlot;
-                            mbar_expect_tx(&bars[B_OUT_FULL + (os ^ 1)], T::kSlot);
-                            tma_load_4d(dst, out_map(ni), &bars[B_OUT_FULL + (os ^ 1)], out_c0(ni), w2, h2, b2);
-                            tma_load_4d(dst + T::kTile, out_map(ni), &bars[B_OUT_FULL + (os ^ 1)], out_c0(ni) + 32, w2, h2, b2);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            float4 q[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                q[j] = *reinterpret_cast<const float4 *>(row + h * T::kTile + ((j ^ sw) * 16));
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int e = 32 * h + 4 * j;
+                                *reinterpret_cast<float4 *>(row + h * T::kTile + ((j ^ sw) * 16)) =
+                                    make_float4(q[j].x + o[e], q[j].y + o[e + 1], q[j].z + o[e + 2], q[j].w + o[e + 3]);
+                            }
                         }
                     }
                 }
-                mbar_wait(&bars[B_OUT_FULL + os], (oc >> 1) & 1);
-                mbar_wait(&bars[B_O_FULL + os], (oc >> 1) & 1);
-                tc_fence_after();
-                float o[kNC];
-#pragma unroll
-                for (int c0 = 0; c0 < kNC; c0 += 16) tmem_ld16(tl + 128 + os * kNC + c0, reinterpret_cast<uint32_t *>(o + c0));
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(&bars[B_O_EMPTY + os]);
-                if (r < LK) {
-                    uint8_t *row = slot + r * 128;
-                    const int sw = r & 7;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float4 *dst = reinterpret_cast<float4 *>(row + (j >> 3) * T::kTile + (((j & 7) ^ sw) * 16));
-                        float4 v = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-                        if (!p.col) { const float4 q = *dst; v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
-                        *dst = v;
-                    }
-                }
                 fence_proxy_async();
-                named_bar_sync(1, 128);
-                if (elected) {
-                    tma_store_4d(out_map(i), slot, out_c0(i), cw, ch, cb);
-                    tma_store_4d(out_map(i), slot + T::kTile, out_c0(i) + 32, cw, ch, cb);
-                    tma_store_commit();
-                }
+                mbar_arrive(&bars[B_STAGED]);
+                CCA_STAMP(4);
             }
         }
-        if (elected) tma_store_wait_all<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -396,6 +411,8 @@ __global__ void __launch_bounds__(256) cca_delta_nhwc_kernel(const float4 *__res
     if (lane == 0) delta[pix] = s;
 }
 
+long long *g_bwd_dbg = nullptr;
+
 template <int LK>
 cudaError_t launch_bwd_pass(const void *dout, const void *q, const void *k, const void *v, const float *lse, const float *delta,
                             void *dq, void *dk, void *dv, Dims d, bool col, cudaStream_t st, const char **why)
@@ -413,6 +430,7 @@ cudaError_t launch_bwd_pass(const void *dout, const void *q, const void *k, cons
     p.B = d.B; p.H = d.H; p.W = d.W; p.C = d.C; p.Cq = d.Cq;
     p.L = col ? d.H : d.W; p.NL = col ? d.W : d.H; p.col = col ? 1 : 0;
     p.lse = lse; p.delta = delta;
+    p.dbg = g_bwd_dbg ? g_bwd_dbg + (col ? 0 : 2560) : nullptr;
     auto kern = cca_tc_bwd_kernel<LK>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<LK>::kBytes);
     if (e != cudaSuccess) return e;
@@ -424,6 +442,8 @@ cudaError_t launch_bwd_pass(const void *dout, const void *q, const void *k, cons
 }
 
 }  // namespace
+
+void set_tc_bwd_debug_buffer(void *p) { g_bwd_dbg = reinterpret_cast<long long *>(p); }
 
 bool tc_backward_supported(Dims d, int dtype) { return tc::shape_supported(d, dtype); }
 
