@@ -48,8 +48,8 @@ template <int LK> struct BwdSmem {
     static constexpr int off_out = off_ld + 2 * T::kSlot;  // 1 out slot (the epilogue has slack; the store warp drives it)
     static constexpr int off_p = off_out + T::kSlot;       // P / dS planes (hi, lo); over-reads land in the operand buffers
     static constexpr int off_op = off_p + T::kP;           // kNOp operand buffers
-    static constexpr int off_tail = off_op + kNOp * T::kOp;// 256 B pad for the 16-row over-read of M=128 MMAs
-    static constexpr int off_bar = off_tail + 256;
+    static constexpr int off_tail = off_op + kNOp * T::kOp;// pad: an M=128 MMA reads (128 - LK) rows past the last plane
+    static constexpr int off_bar = off_tail + (128 - LK) * 16 + 256;
     static constexpr int kBytes = off_bar + 320;
     static_assert(kBytes <= 232448, "shared memory budget");
 };

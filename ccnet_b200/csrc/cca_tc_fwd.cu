@@ -89,8 +89,8 @@ template <int LK> struct FwdSmem {
     static constexpr int off_ld = 0;                          // kNLd load slots
     static constexpr int off_out = off_ld + kNLd * T::kSlot;  // kNOut out slots
     static constexpr int off_op = off_out + kNOut * T::kSlot; // 2 operand buffers
-    static constexpr int off_tail = off_op + 2 * T::kOp;      // 256 B pad: M=128 MMAs read 16 rows past LK rows
-    static constexpr int off_scale = off_tail + 256;          // float2 (sa, sb) [2][128]: softmax group -> epilogue group
+    static constexpr int off_tail = off_op + 2 * T::kOp;      // pad: an M=128 MMA reads (128 - LK) rows past the last plane
+    static constexpr int off_scale = off_tail + (128 - LK) * 16;          // float2 (sa, sb) [2][128]: softmax group -> epilogue group
     static constexpr int off_bar = off_scale + 2 * 128 * 8;
     static constexpr int kBytes = off_bar + 320;
     static_assert(kBytes <= 232448, "shared memory budget");
