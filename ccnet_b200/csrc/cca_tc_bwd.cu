@@ -23,7 +23,8 @@ namespace cca {
 namespace {
 using namespace tc;
 
-constexpr int kTmemCols = 256;      // S / dP: [0,128)   O0: [128,192)   O1: [192,256)
+constexpr int kTmemCols = 512;      // S / dP double buffer: [0,128) [128,256)   O0: [256,320)   O1: [320,384)
+constexpr int kTmemO = 256;
 constexpr int kRegsSoft = 152, kRegsEpi = 144;
 static_assert(reg_pool_ok(kRegsSoft, kRegsEpi), "setmaxnreg pool");
 
@@ -54,9 +55,9 @@ template <int LK> struct BwdSmem {
     static_assert(kBytes <= 232448, "shared memory budget");
 };
 
-enum { B_LD_FULL = 0, B_LD_EMPTY = 2, B_OP_FULL = 4, B_OP_EMPTY = 7, B_S_FULL = 10, B_S_EMPTY = 11, B_P_FULL = 12,
-       B_P_EMPTY = 13, B_O_FULL = 14, B_O_EMPTY = 16, B_OUT_FULL = 18, B_STAGED = 19, B_DP_FULL = 20, B_DS_FULL = 21,
-       B_COUNT = 22 };
+enum { B_LD_FULL = 0, B_LD_EMPTY = 2, B_OP_FULL = 4, B_OP_EMPTY = 7, B_S_FULL = 10, B_S_EMPTY = 12, B_P_FULL = 14,
+       B_P_EMPTY = 15, B_O_FULL = 16, B_O_EMPTY = 18, B_OUT_FULL = 20, B_STAGED = 21, B_DP_FULL = 22, B_DS_FULL = 23,
+       B_COUNT = 24 };
 
 // Per line the ring carries  Q K (V_n dO_n)* Q K ; item g is converted into operand buffer g % 3, so the conversion of
 // the next chunk overlaps the MMAs of the current one.  MMAs per line: S (phase A), per chunk dP += dO V^T then
@@ -89,7 +90,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
         }
         for (int i = 0; i < kNOp; ++i) { mbar_init(&bars[B_OP_FULL + i], kConvThreads); mbar_init(&bars[B_OP_EMPTY + i], 1); }
         mbar_init(&bars[B_OUT_FULL], 1); mbar_init(&bars[B_STAGED], 128);
-        mbar_init(&bars[B_S_FULL], 1);   mbar_init(&bars[B_S_EMPTY], 128);
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_S_FULL + i], 1); mbar_init(&bars[B_S_EMPTY + i], 128); }
         mbar_init(&bars[B_P_FULL], 128); mbar_init(&bars[B_P_EMPTY], 1);
         mbar_init(&bars[B_DP_FULL], 1);  mbar_init(&bars[B_DS_FULL], 128);
         fence_mbar_init();
@@ -119,22 +120,27 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
             if (lane == 0) {
                 uint32_t g = 0;
                 int dbg_n = 0;
-                for (int k = 0; k < nk; ++k) {
+                auto emit = [&](const CUtensorMap *m, int c0, int line) {
                     int cw, ch, cb;
-                    line_coords(line_of(k), cw, ch, cb);
-                    for (int item = 0; item < NI; ++item, ++g) {
-                        const int slot = g & 1;
-                        mbar_wait(&bars[B_LD_EMPTY + slot], ((g >> 1) & 1) ^ 1);
-                        CCA_STAMP(0);
-                        uint8_t *dst = smem + S::off_ld + slot * T::kSlot;
-                        mbar_expect_tx(&bars[B_LD_FULL + slot], T::kSlot);
-                        const CUtensorMap *m;
-                        int c0 = 0;
-                        if (item < 2 || item >= 2 + 2 * NCH) m = (item & 1) ? &mk : &mq;
-                        else { m = (item & 1) ? &mdo : &mv; c0 = ((item - 2) >> 1) * kNC; }
-                        tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, cb);
-                        tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, cb);
-                    }
+                    line_coords(line, cw, ch, cb);
+                    const int slot = g & 1;
+                    mbar_wait(&bars[B_LD_EMPTY + slot], ((g >> 1) & 1) ^ 1);
+                    CCA_STAMP(0);
+                    uint8_t *dst = smem + S::off_ld + slot * T::kSlot;
+                    mbar_expect_tx(&bars[B_LD_FULL + slot], T::kSlot);
+                    tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, cb);
+                    tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, cb);
+                    ++g;
+                };
+                // ring:  Q0 K0 | (V dO)* Q1 K1 Q0 K0 | (V dO)* Q2 K2 Q1 K1 | ...   (S of the next line is issued while the
+                // dS of the current one is being computed; Q,K of the current line come back for dQ/dK)
+                emit(&mq, 0, line_of(0));
+                emit(&mk, 0, line_of(0));
+                for (int k = 0; k < nk; ++k) {
+                    for (int n = 0; n < NCH; ++n) { emit(&mv, n * kNC, line_of(k)); emit(&mdo, n * kNC, line_of(k)); }
+                    if (k + 1 < nk) { emit(&mq, 0, line_of(k + 1)); emit(&mk, 0, line_of(k + 1)); }
+                    emit(&mq, 0, line_of(k));
+                    emit(&mk, 0, line_of(k));
                 }
             }
         } else if (warp == kWarpMma) {
@@ -149,24 +155,25 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
             auto opb = [&](uint32_t g) { return op_base + (g % kNOp) * T::kOp; };
             auto wait_op = [&](uint32_t g) { mbar_wait(&bars[B_OP_FULL + g % kNOp], (g / kNOp) & 1); };
             auto free_op = [&](uint32_t g) { commit_to(&bars[B_OP_EMPTY + g % kNOp]); };
+            auto issue_s = [&](int k) {                       // S(k) = Q K^T into S buffer k&1
+                const uint32_t q = opb(u), kk = opb(u + 1);
+                wait_op(u); wait_op(u + 1);
+                mbar_wait(&bars[B_S_EMPTY + (k & 1)], ((k >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem + (k & 1) * 128;
+                for (int ks = 0; ks < KQ; ++ks) {
+                    const uint32_t ao = ks * 2 * T::kPlane;
+                    mma_split3(d, smem_desc(q + ao, T::kPlane, 128), smem_desc(q + LO8 + ao, T::kPlane, 128),
+                               smem_desc(kk + ao, T::kPlane, 128), smem_desc(kk + LO8 + ao, T::kPlane, 128), id_kk_s, ks > 0);
+                }
+                commit_to(&bars[B_S_FULL + (k & 1)]);
+                free_op(u); free_op(u + 1);
+                u += 2;
+            };
+            issue_s(0);
             for (int k = 0; k < nk; ++k) {
                 CCA_STAMP(2);
-                // ---- phase A: S = Q K^T
-                {
-                    const uint32_t q = opb(u), kk = opb(u + 1);
-                    wait_op(u); wait_op(u + 1);
-                    mbar_wait(&bars[B_S_EMPTY], (k & 1) ^ 1);
-                    tc_fence_after();
-                    for (int ks = 0; ks < KQ; ++ks) {
-                        const uint32_t ao = ks * 2 * T::kPlane;
-                        mma_split3(tmem, smem_desc(q + ao, T::kPlane, 128), smem_desc(q + LO8 + ao, T::kPlane, 128),
-                                   smem_desc(kk + ao, T::kPlane, 128), smem_desc(kk + LO8 + ao, T::kPlane, 128), id_kk_s, ks > 0);
-                    }
-                    commit_to(&bars[B_S_FULL]);
-                    free_op(u); free_op(u + 1);
-                    u += 2;
-                }
-                CCA_STAMP(2);
+                const uint32_t sdp = tmem + (k & 1) * 128;        // S(k), then dP(k)
                 mbar_wait(&bars[B_P_FULL], k & 1);
                 CCA_STAMP(2);
                 // ---- phase B: per chunk  dP += dO V^T  and  dV = P^T dO
@@ -174,18 +181,19 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                     const uint32_t vb = opb(u), db = opb(u + 1);
                     wait_op(u); wait_op(u + 1);
                     tc_fence_after();
-                    mma_split3_loop<kNC / 16>(tmem, db, db + LO8, 2 * T::kPlane, T::kPlane, 128,
+                    mma_split3_loop<kNC / 16>(sdp, db, db + LO8, 2 * T::kPlane, T::kPlane, 128,
                                               vb, vb + LO8, 2 * T::kPlane, T::kPlane, 128, id_kk_s, n > 0);
                     free_op(u);                                   // V is only needed by dP
                     mbar_wait(&bars[B_O_EMPTY + (oc & 1)], ((oc >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    mma_split3_loop<LK / 16>(tmem + 128 + (oc & 1) * kNC, pb, pb + LOP, 256, 128, T::kPlane,
+                    mma_split3_loop<LK / 16>(tmem + kTmemO + (oc & 1) * kNC, pb, pb + LOP, 256, 128, T::kPlane,
                                              db, db + LO8, 256, 128, T::kPlane, id_mn_mn, false);
                     commit_to(&bars[B_O_FULL + (oc & 1)]);
                     free_op(u + 1);
                     CCA_STAMP(2);
                 }
                 commit_to(&bars[B_DP_FULL]);
+                if (k + 1 < nk) issue_s(k + 1);                   // overlaps the dS computation of this line
                 // ---- phase D: dQ = dS K,  dK = dS^T Q      (dS in the P planes)
                 mbar_wait(&bars[B_DS_FULL], k & 1);
                 CCA_STAMP(2);
@@ -194,14 +202,14 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                     wait_op(u); wait_op(u + 1);
                     mbar_wait(&bars[B_O_EMPTY + (oc & 1)], ((oc >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    mma_split3_loop<LK / 16>(tmem + 128 + (oc & 1) * kNC, pb, pb + LOP, 2 * T::kPlane, T::kPlane, 128,
+                    mma_split3_loop<LK / 16>(tmem + kTmemO + (oc & 1) * kNC, pb, pb + LOP, 2 * T::kPlane, T::kPlane, 128,
                                              kk, kk + LO8, 256, 128, T::kPlane, id_k_mn, false);
                     commit_to(&bars[B_O_FULL + (oc & 1)]);
                     free_op(u + 1);
                     ++oc;
                     mbar_wait(&bars[B_O_EMPTY + (oc & 1)], ((oc >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    mma_split3_loop<LK / 16>(tmem + 128 + (oc & 1) * kNC, pb, pb + LOP, 256, 128, T::kPlane,
+                    mma_split3_loop<LK / 16>(tmem + kTmemO + (oc & 1) * kNC, pb, pb + LOP, 256, 128, T::kPlane,
                                              q, q + LO8, 256, 128, T::kPlane, id_mn_mn, false);
                     commit_to(&bars[B_O_FULL + (oc & 1)]);
                     free_op(u);
@@ -272,14 +280,15 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
             }
             uint8_t *ph = smem + S::off_p + r * 16, *pl = ph + T::kPP * T::kPlane;
             // ---------------- P = exp(S - lse)
+            const uint32_t tsd = tl + (k & 1) * 128;           // S(k) / dP(k) buffer
             CCA_STAMP(3);
-            mbar_wait(&bars[B_S_FULL], k & 1);
+            mbar_wait(&bars[B_S_FULL + (k & 1)], (k >> 1) & 1);
             tc_fence_after();
             CCA_STAMP(3);
             {
                 float s[LK];
 #pragma unroll
-                for (int c0 = 0; c0 < LK; c0 += 16) tmem_ld16(tl + c0, reinterpret_cast<uint32_t *>(s + c0));
+                for (int c0 = 0; c0 < LK; c0 += 16) tmem_ld16(tsd + c0, reinterpret_cast<uint32_t *>(s + c0));
                 tmem_ld_wait();
                 tc_fence_before();
 #pragma unroll
@@ -308,10 +317,10 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
             {
                 float dp[LK];
 #pragma unroll
-                for (int c0 = 0; c0 < LK; c0 += 16) tmem_ld16(tl + c0, reinterpret_cast<uint32_t *>(dp + c0));
+                for (int c0 = 0; c0 < LK; c0 += 16) tmem_ld16(tsd + c0, reinterpret_cast<uint32_t *>(dp + c0));
                 tmem_ld_wait();
                 tc_fence_before();
-                mbar_arrive(&bars[B_S_EMPTY]);
+                mbar_arrive(&bars[B_S_EMPTY + (k & 1)]);
                 if (r < LK) {
 #pragma unroll
                     for (int kc = 0; kc < T::kPP; ++kc) {
@@ -354,7 +363,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                 CCA_STAMP(4);
                 float o[kNC];
 #pragma unroll
-                for (int c0 = 0; c0 < kNC; c0 += 16) tmem_ld16(tl + 128 + ob * kNC + c0, reinterpret_cast<uint32_t *>(o + c0));
+                for (int c0 = 0; c0 < kNC; c0 += 16) tmem_ld16(tl + kTmemO + ob * kNC + c0, reinterpret_cast<uint32_t *>(o + c0));
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(&bars[B_O_EMPTY + ob]);
