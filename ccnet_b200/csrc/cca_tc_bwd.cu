@@ -4,7 +4,7 @@
 // attention matrix is recomputed per line from (q, k, lse), never stored.  As in the forward, a row and a
 // column of a channels-last image are the same object, so one kernel runs twice:
 //   pass 1 (columns, self entry masked): dq, dk, dv  = column-branch contributions
-//   pass 2 (rows)                      : dq, dk, dv += row-branch contributions (partials re-read by TMA)
+//   pass 2 (rows)                      : dq, dk, dv += row-branch contributions (TMA reduce-add, performed at L2)
 // Each line CTA owns all outputs of its line: no atomics, deterministic.
 //
 // Per line (jq = query pixel, jk = key pixel, both < L <= LK):
@@ -230,15 +230,15 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                     line_coords(line_of(k), cw, ch, cb);
                     // slot is free once the previous store has been read out of shared memory
                     tma_store_wait_read<0>();
-                    if (p.col) mbar_arrive(&bars[B_OUT_FULL]);
-                    else {                                         // row pass: fetch the column-pass partial to accumulate onto
-                        mbar_expect_tx(&bars[B_OUT_FULL], T::kSlot);
-                        tma_load_4d(slot, out_map(i), &bars[B_OUT_FULL], out_c0(i), cw, ch, cb);
-                        tma_load_4d(slot + T::kTile, out_map(i), &bars[B_OUT_FULL], out_c0(i) + 32, cw, ch, cb);
-                    }
+                    mbar_arrive(&bars[B_OUT_FULL]);
                     mbar_wait(&bars[B_STAGED], c & 1);
-                    tma_store_4d(out_map(i), slot, out_c0(i), cw, ch, cb);
-                    tma_store_4d(out_map(i), slot + T::kTile, out_c0(i) + 32, cw, ch, cb);
+                    if (p.col) {                                   // column pass defines dq/dk/dv ...
+                        tma_store_4d(out_map(i), slot, out_c0(i), cw, ch, cb);
+                        tma_store_4d(out_map(i), slot + T::kTile, out_c0(i) + 32, cw, ch, cb);
+                    } else {                                       // ... the row pass accumulates onto them (TMA reduce-add at L2)
+                        tma_reduce_add_4d(out_map(i), slot, out_c0(i), cw, ch, cb);
+                        tma_reduce_add_4d(out_map(i), slot + T::kTile, out_c0(i) + 32, cw, ch, cb);
+                    }
                     tma_store_commit();
                 }
                 tma_store_wait_all<0>();
@@ -370,26 +370,10 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                 if (r < p.L) {                                        // rows >= L are clipped by the TMA store
                     uint8_t *row = slot + r * 128;
                     const int sw = r & 7;
-                    if (p.col) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            *reinterpret_cast<float4 *>(row + (j >> 3) * T::kTile + (((j & 7) ^ sw) * 16)) =
-                                make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-                    } else {
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            float4 q[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                q[j] = *reinterpret_cast<const float4 *>(row + h * T::kTile + ((j ^ sw) * 16));
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const int e = 32 * h + 4 * j;
-                                *reinterpret_cast<float4 *>(row + h * T::kTile + ((j ^ sw) * 16)) =
-                                    make_float4(q[j].x + o[e], q[j].y + o[e + 1], q[j].z + o[e + 2], q[j].w + o[e + 3]);
-                            }
-                        }
-                    }
+                    for (int j = 0; j < 16; ++j)
+                        *reinterpret_cast<float4 *>(row + (j >> 3) * T::kTile + (((j & 7) ^ sw) * 16)) =
+                            make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
                 }
                 fence_proxy_async();
                 mbar_arrive(&bars[B_STAGED]);
