@@ -137,7 +137,6 @@ __global__ void __launch_bounds__(128) tma_probe(const __grid_constant__ CUtenso
         tma_store_commit();
         tma_store_wait_all<0>();
         tma_reduce_add_4d(&map_out, srow, c0, 0, h, 0);      // Y += tile  -> Y == 2 * X on the tile
-        tma_reduce_add_4d(&map_out, scol, c0, w, 0, 0);      // column box added onto column w
         tma_store_commit();
         tma_store_wait_all<0>();
     }
@@ -225,7 +224,7 @@ int main()
         const bool inc = c >= (size_t)c0 && c < (size_t)c0 + 32 && bb == 0;
         float e = 0.f;
         if (inc && hh == (size_t)h) e += 2.f * X[i];             // store + reduce-add of the row tile
-        if (inc && ww == (size_t)w) e += X[i];                   // reduce-add of the column tile
+        (void)ww;
         if (Y[i] != e) ++bad_s;
     }
     printf("TMA row box  SW128 + OOB zero fill : %s (%d mismatches)\n", bad_r ? "MISMATCH" : "OK", bad_r);
