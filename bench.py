@@ -307,9 +307,16 @@ def run_ours(args):
     dom_is_bwd = b_avg >= f_avg
     dom_bytes, dom_ms = (bytes_b, b_avg) if dom_is_bwd else (bytes_f, f_avg)
     ach = dom_bytes / (dom_ms * 1e-3) / 1e9
+    # DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of one op call from the ncu --set full capture of
+    # tools/run_op.py committed as profiles/r01c_tc_ncu_summary.txt (B=8, C=512, 97x97, fp32, tensor-core kernels)
+    ncu_traffic = None
+    if (B, C, H, W) == (8, 512, 97, 97) and dtype == torch.float32 and op_layout == "channels_last":
+        ncu_traffic = {"fwd": 751.4e6, "bwd": 1579.3e6}
     roofline = {"bound": "hbm", "kernel": "cca backward op (delta + column pass + row pass)" if dom_is_bwd
                 else "cca forward op (column pass + row pass)",
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": (ncu_traffic["bwd" if dom_is_bwd else "fwd"] if ncu_traffic else None),
+                "traffic_source": "ncu --set full, profiles/r01c_tc_ncu_summary.txt (sum over the launches of one op call)",
                 "peak_source": peak_src, "launches_per_op": nb if dom_is_bwd else nf,
                 "op_fwd": {"ms": f_avg, "ms_min": f_min, "alg_bytes": bytes_f, "gbs": bytes_f / f_avg / 1e6,
                            "frac": bytes_f / f_avg / 1e6 / peak, "launches": nf},
