@@ -43,8 +43,8 @@ struct BwdParams {
 
 constexpr int kNOp = 3;             // rotating operand buffers
 
-template <int LK> struct BwdSmem {
-    using T = Tiles<LK>;
+template <int LK, bool BF> struct BwdSmem {
+    using T = Tiles<LK, BF>;
     static constexpr int off_ld = 0;                       // 2 load slots
     static constexpr int off_out = off_ld + 2 * T::kSlot;  // 1 out slot (the epilogue has slack; the store warp drives it)
     static constexpr int off_p = off_out + T::kSlot;       // P / dS planes (hi, lo); over-reads land in the operand buffers
@@ -63,15 +63,16 @@ enum { B_LD_FULL = 0, B_LD_EMPTY = 2, B_OP_FULL = 4, B_OP_EMPTY = 7, B_S_FULL = 
 // the next chunk overlaps the MMAs of the current one.  MMAs per line: S (phase A), per chunk dP += dO V^T then
 // dV = P^T dO (phase B; the V buffer is released right after the dP MMAs), dS by the P/dS group (phase C),
 // dQ = dS K and dK = dS^T Q (phase D).
-template <int LK>
+template <int LK, bool BF>
 __global__ void __launch_bounds__(kThreads, 1)
 cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
                   const __grid_constant__ CUtensorMap mv, const __grid_constant__ CUtensorMap mdo,
                   const __grid_constant__ CUtensorMap mdq, const __grid_constant__ CUtensorMap mdk,
                   const __grid_constant__ CUtensorMap mdv, BwdParams p)
 {
-    using T = Tiles<LK>;
-    using S = BwdSmem<LK>;
+    using T = Tiles<LK, BF>;
+    using S = BwdSmem<LK, BF>;
+    constexpr int TERMS = BF ? 1 : 3;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S::off_bar);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::off_bar + 8 * B_COUNT);
@@ -129,7 +130,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                     uint8_t *dst = smem + S::off_ld + slot * T::kSlot;
                     mbar_expect_tx(&bars[B_LD_FULL + slot], T::kSlot);
                     tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, cb);
-                    tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, cb);
+                    if constexpr (!BF) tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, cb);
                     ++g;
                 };
                 // ring:  Q0 K0 | (V dO)* Q1 K1 Q0 K0 | (V dO)* Q2 K2 Q1 K1 | ...   (S of the next line is issued while the
@@ -163,8 +164,8 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                 const uint32_t d = tmem + (k & 1) * 128;
                 for (int ks = 0; ks < KQ; ++ks) {
                     const uint32_t ao = ks * 2 * T::kPlane;
-                    mma_split3(d, smem_desc(q + ao, T::kPlane, 128), smem_desc(q + LO8 + ao, T::kPlane, 128),
-                               smem_desc(kk + ao, T::kPlane, 128), smem_desc(kk + LO8 + ao, T::kPlane, 128), id_kk_s, ks > 0);
+                    mma_split3<TERMS>(d, smem_desc(q + ao, T::kPlane, 128), smem_desc(q + LO8 + ao, T::kPlane, 128),
+                                      smem_desc(kk + ao, T::kPlane, 128), smem_desc(kk + LO8 + ao, T::kPlane, 128), id_kk_s, ks > 0);
                 }
                 commit_to(&bars[B_S_FULL + (k & 1)]);
                 free_op(u); free_op(u + 1);
@@ -181,12 +182,12 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                     const uint32_t vb = opb(u), db = opb(u + 1);
                     wait_op(u); wait_op(u + 1);
                     tc_fence_after();
-                    mma_split3_loop<kNC / 16>(sdp, db, db + LO8, 2 * T::kPlane, T::kPlane, 128,
+                    mma_split3_loop<kNC / 16, TERMS>(sdp, db, db + LO8, 2 * T::kPlane, T::kPlane, 128,
                                               vb, vb + LO8, 2 * T::kPlane, T::kPlane, 128, id_kk_s, n > 0);
                     free_op(u);                                   // V is only needed by dP
                     mbar_wait(&bars[B_O_EMPTY + (oc & 1)], ((oc >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    mma_split3_loop<LK / 16>(tmem + kTmemO + (oc & 1) * kNC, pb, pb + LOP, 256, 128, T::kPlane,
+                    mma_split3_loop<LK / 16, TERMS>(tmem + kTmemO + (oc & 1) * kNC, pb, pb + LOP, 256, 128, T::kPlane,
                                              db, db + LO8, 256, 128, T::kPlane, id_mn_mn, false);
                     commit_to(&bars[B_O_FULL + (oc & 1)]);
                     free_op(u + 1);
@@ -202,14 +203,14 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                     wait_op(u); wait_op(u + 1);
                     mbar_wait(&bars[B_O_EMPTY + (oc & 1)], ((oc >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    mma_split3_loop<LK / 16>(tmem + kTmemO + (oc & 1) * kNC, pb, pb + LOP, 2 * T::kPlane, T::kPlane, 128,
+                    mma_split3_loop<LK / 16, TERMS>(tmem + kTmemO + (oc & 1) * kNC, pb, pb + LOP, 2 * T::kPlane, T::kPlane, 128,
                                              kk, kk + LO8, 256, 128, T::kPlane, id_k_mn, false);
                     commit_to(&bars[B_O_FULL + (oc & 1)]);
                     free_op(u + 1);
                     ++oc;
                     mbar_wait(&bars[B_O_EMPTY + (oc & 1)], ((oc >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    mma_split3_loop<LK / 16>(tmem + kTmemO + (oc & 1) * kNC, pb, pb + LOP, 256, 128, T::kPlane,
+                    mma_split3_loop<LK / 16, TERMS>(tmem + kTmemO + (oc & 1) * kNC, pb, pb + LOP, 256, 128, T::kPlane,
                                              q, q + LO8, 256, 128, T::kPlane, id_mn_mn, false);
                     commit_to(&bars[B_O_FULL + (oc & 1)]);
                     free_op(u);
@@ -234,10 +235,10 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                     mbar_wait(&bars[B_STAGED], c & 1);
                     if (p.col) {                                   // column pass defines dq/dk/dv ...
                         tma_store_4d(out_map(i), slot, out_c0(i), cw, ch, cb);
-                        tma_store_4d(out_map(i), slot + T::kTile, out_c0(i) + 32, cw, ch, cb);
+                        if constexpr (!BF) tma_store_4d(out_map(i), slot + T::kTile, out_c0(i) + 32, cw, ch, cb);
                     } else {                                       // ... the row pass accumulates onto them (TMA reduce-add at L2)
                         tma_reduce_add_4d(out_map(i), slot, out_c0(i), cw, ch, cb);
-                        tma_reduce_add_4d(out_map(i), slot + T::kTile, out_c0(i) + 32, cw, ch, cb);
+                        if constexpr (!BF) tma_reduce_add_4d(out_map(i), slot + T::kTile, out_c0(i) + 32, cw, ch, cb);
                     }
                     tma_store_commit();
                 }
@@ -256,7 +257,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
             CCA_STAMP(1);
             mbar_wait(&bars[B_OP_EMPTY + ob], ((g / kNOp) & 1) ^ 1);
             CCA_STAMP(1);
-            convert_slot<LK>(smem + S::off_ld + slot * T::kSlot, smem + S::off_op + ob * T::kOp, t);
+            convert_slot<LK, BF>(smem + S::off_ld + slot * T::kSlot, smem + S::off_op + ob * T::kOp, t);
             fence_proxy_async();
             mbar_arrive(&bars[B_OP_FULL + ob]);
             mbar_arrive(&bars[B_LD_EMPTY + slot]);
@@ -300,10 +301,16 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                 if (r < LK) {
 #pragma unroll
                     for (int kc = 0; kc < T::kPP; ++kc) {
-                        uint4 hi, lo;
-                        split8(s + kc * 8, hi, lo);
-                        *reinterpret_cast<uint4 *>(ph + kc * T::kPlane) = hi;
-                        *reinterpret_cast<uint4 *>(pl + kc * T::kPlane) = lo;
+                        const float *v8 = s + kc * 8;
+                        if constexpr (BF) {
+                            *reinterpret_cast<uint4 *>(ph + kc * T::kPlane) =
+                                make_uint4(pack_bf16(v8[0], v8[1]), pack_bf16(v8[2], v8[3]), pack_bf16(v8[4], v8[5]), pack_bf16(v8[6], v8[7]));
+                        } else {
+                            uint4 hi, lo;
+                            split8(v8, hi, lo);
+                            *reinterpret_cast<uint4 *>(ph + kc * T::kPlane) = hi;
+                            *reinterpret_cast<uint4 *>(pl + kc * T::kPlane) = lo;
+                        }
                     }
                 }
                 fence_proxy_async();
@@ -325,7 +332,8 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
 #pragma unroll
                     for (int kc = 0; kc < T::kPP; ++kc) {
                         const uint4 hi = *reinterpret_cast<const uint4 *>(ph + kc * T::kPlane);
-                        const uint4 lo = *reinterpret_cast<const uint4 *>(pl + kc * T::kPlane);
+                        uint4 lo = make_uint4(0, 0, 0, 0);
+                        if constexpr (!BF) lo = *reinterpret_cast<const uint4 *>(pl + kc * T::kPlane);
                         const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
                         float ds[8];
 #pragma unroll
@@ -334,10 +342,15 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                             ds[2 * e] = p0 * (dp[kc * 8 + 2 * e] - dl);
                             ds[2 * e + 1] = p1 * (dp[kc * 8 + 2 * e + 1] - dl);
                         }
-                        uint4 dh, dlo;
-                        split8(ds, dh, dlo);
-                        *reinterpret_cast<uint4 *>(ph + kc * T::kPlane) = dh;
-                        *reinterpret_cast<uint4 *>(pl + kc * T::kPlane) = dlo;
+                        if constexpr (BF) {
+                            *reinterpret_cast<uint4 *>(ph + kc * T::kPlane) =
+                                make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7]));
+                        } else {
+                            uint4 dh, dlo;
+                            split8(ds, dh, dlo);
+                            *reinterpret_cast<uint4 *>(ph + kc * T::kPlane) = dh;
+                            *reinterpret_cast<uint4 *>(pl + kc * T::kPlane) = dlo;
+                        }
                     }
                 }
                 fence_proxy_async();
@@ -370,10 +383,18 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                 if (r < p.L) {                                        // rows >= L are clipped by the TMA store
                     uint8_t *row = slot + r * 128;
                     const int sw = r & 7;
+                    if constexpr (BF) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        *reinterpret_cast<float4 *>(row + (j >> 3) * T::kTile + (((j & 7) ^ sw) * 16)) =
-                            make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<uint4 *>(row + ((j ^ sw) * 16)) =
+                                make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]),
+                                           pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            *reinterpret_cast<float4 *>(row + (j >> 3) * T::kTile + (((j & 7) ^ sw) * 16)) =
+                                make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    }
                 }
                 fence_proxy_async();
                 mbar_arrive(&bars[B_STAGED]);
@@ -404,17 +425,37 @@ __global__ void __launch_bounds__(256) cca_delta_nhwc_kernel(const float4 *__res
     if (lane == 0) delta[pix] = s;
 }
 
+// bf16 variant: 8 channels per 16-byte load
+__global__ void __launch_bounds__(256) cca_delta_nhwc_bf16_kernel(const uint4 *__restrict__ dout, const uint4 *__restrict__ out,
+                                                                  float *__restrict__ delta, long npix, int c8)
+{
+    const long pix = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (pix >= npix) return;
+    const int lane = threadIdx.x & 31;
+    const uint4 *a = dout + pix * c8, *b = out + pix * c8;
+    float s = 0.f;
+    for (int i = lane; i < c8; i += 32) {
+        const uint4 x = __ldg(a + i), y = __ldg(b + i);
+        const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s += bf_lo(xw[e]) * bf_lo(yw[e]) + bf_hi(xw[e]) * bf_hi(yw[e]);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) delta[pix] = s;
+}
+
 long long *g_bwd_dbg = nullptr;
 
-template <int LK>
+template <int LK, bool BF>
 cudaError_t launch_bwd_pass(const void *dout, const void *q, const void *k, const void *v, const float *lse, const float *delta,
                             void *dq, void *dk, void *dv, Dims d, bool col, cudaStream_t st, const char **why)
 {
     CUtensorMap mq, mk, mv, mdo, mdq, mdk, mdv;
-    const bool ok = make_map(&mq, q, d.B, d.H, d.W, d.Cq, LK, col) && make_map(&mk, k, d.B, d.H, d.W, d.Cq, LK, col) &&
-                    make_map(&mv, v, d.B, d.H, d.W, d.C, LK, col) && make_map(&mdo, dout, d.B, d.H, d.W, d.C, LK, col) &&
-                    make_map(&mdq, dq, d.B, d.H, d.W, d.Cq, LK, col) && make_map(&mdk, dk, d.B, d.H, d.W, d.Cq, LK, col) &&
-                    make_map(&mdv, dv, d.B, d.H, d.W, d.C, LK, col);
+    const bool ok = make_map(&mq, q, d.B, d.H, d.W, d.Cq, LK, col, BF) && make_map(&mk, k, d.B, d.H, d.W, d.Cq, LK, col, BF) &&
+                    make_map(&mv, v, d.B, d.H, d.W, d.C, LK, col, BF) && make_map(&mdo, dout, d.B, d.H, d.W, d.C, LK, col, BF) &&
+                    make_map(&mdq, dq, d.B, d.H, d.W, d.Cq, LK, col, BF) && make_map(&mdk, dk, d.B, d.H, d.W, d.Cq, LK, col, BF) &&
+                    make_map(&mdv, dv, d.B, d.H, d.W, d.C, LK, col, BF);
     if (!ok) {
         if (why) *why = "cuTensorMapEncodeTiled failed";
         return cudaErrorInvalidValue;
@@ -424,12 +465,12 @@ cudaError_t launch_bwd_pass(const void *dout, const void *q, const void *k, cons
     p.L = col ? d.H : d.W; p.NL = col ? d.W : d.H; p.col = col ? 1 : 0;
     p.lse = lse; p.delta = delta;
     p.dbg = g_bwd_dbg ? g_bwd_dbg + (col ? 0 : 2560) : nullptr;
-    auto kern = cca_tc_bwd_kernel<LK>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<LK>::kBytes);
+    auto kern = cca_tc_bwd_kernel<LK, BF>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<LK, BF>::kBytes);
     if (e != cudaSuccess) return e;
     const int lines = d.B * p.NL;
     const int grid = lines < sm_count() ? lines : sm_count();
-    kern<<<grid, kThreads, BwdSmem<LK>::kBytes, st>>>(mq, mk, mv, mdo, mdq, mdk, mdv, p);
+    kern<<<grid, kThreads, BwdSmem<LK, BF>::kBytes, st>>>(mq, mk, mv, mdo, mdq, mdk, mdv, p);
     count_launch();
     return cudaGetLastError();
 }
@@ -440,24 +481,33 @@ void set_tc_bwd_debug_buffer(void *p) { g_bwd_dbg = reinterpret_cast<long long *
 
 bool tc_backward_supported(Dims d, int dtype) { return tc::shape_supported(d, dtype); }
 
-// all tensors channels-last (NHWC) fp32; ws = delta [B,H,W]
+// all tensors channels-last (NHWC), fp32 or bf16; ws = delta [B,H,W]
 cudaError_t tc_backward(const void *dout, const void *q, const void *k, const void *v, const void *out, const float *lse,
                         void *dq, void *dk, void *dv, void *ws, Dims d, int dtype, cudaStream_t st, const char **why)
 {
-    (void)dtype;
     float *delta = reinterpret_cast<float *>(ws);
     const long npix = (long)d.B * d.H * d.W;
-    cca_delta_nhwc_kernel<<<(unsigned)((npix + 7) / 8), 256, 0, st>>>(reinterpret_cast<const float4 *>(dout),
-                                                                     reinterpret_cast<const float4 *>(out), delta, npix, d.C / 4);
+    const bool bf = dtype == CCA_BF16;
+    const unsigned dgrid = (unsigned)((npix + 7) / 8);
+    if (bf)
+        cca_delta_nhwc_bf16_kernel<<<dgrid, 256, 0, st>>>(reinterpret_cast<const uint4 *>(dout), reinterpret_cast<const uint4 *>(out),
+                                                          delta, npix, d.C / 8);
+    else
+        cca_delta_nhwc_kernel<<<dgrid, 256, 0, st>>>(reinterpret_cast<const float4 *>(dout), reinterpret_cast<const float4 *>(out),
+                                                     delta, npix, d.C / 4);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    e = lk_for(d.H) == 80 ? launch_bwd_pass<80>(dout, q, k, v, lse, delta, dq, dk, dv, d, true, st, why)
-                          : launch_bwd_pass<112>(dout, q, k, v, lse, delta, dq, dk, dv, d, true, st, why);
+    auto go = [&](int lk, bool col) {
+        if (bf)
+            return lk == 80 ? launch_bwd_pass<80, true>(dout, q, k, v, lse, delta, dq, dk, dv, d, col, st, why)
+                            : launch_bwd_pass<112, true>(dout, q, k, v, lse, delta, dq, dk, dv, d, col, st, why);
+        return lk == 80 ? launch_bwd_pass<80, false>(dout, q, k, v, lse, delta, dq, dk, dv, d, col, st, why)
+                        : launch_bwd_pass<112, false>(dout, q, k, v, lse, delta, dq, dk, dv, d, col, st, why);
+    };
+    e = go(lk_for(d.H), true);
     if (e != cudaSuccess) return e;
-    e = lk_for(d.W) == 80 ? launch_bwd_pass<80>(dout, q, k, v, lse, delta, dq, dk, dv, d, false, st, why)
-                          : launch_bwd_pass<112>(dout, q, k, v, lse, delta, dq, dk, dv, d, false, st, why);
-    return e;
+    return go(lk_for(d.W), false);
 }
 
 }  // namespace cca

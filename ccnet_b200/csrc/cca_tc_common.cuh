@@ -34,13 +34,16 @@ constexpr bool reg_pool_ok(int soft, int epi)
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
-template <int LK> struct Tiles {
-    static constexpr int kTile = LK * 128;             // [LK px][32 fp32], SWIZZLE_128B
-    static constexpr int kSlot = 2 * kTile;            // 64 channels
+// BF = false: fp32 I/O, every operand split into bf16 hi + lo (3 MMAs per product).
+// BF = true : bf16 I/O, operands used as they are (1 MMA per product); a 64-channel chunk is ONE 128-byte-wide TMA tile.
+template <int LK, bool BF = false> struct Tiles {
+    static constexpr int kTile = LK * 128;             // [LK px][128 B] = 32 fp32 or 64 bf16 channels, SWIZZLE_128B
+    static constexpr int kSlot = BF ? kTile : 2 * kTile; // 64 channels
     static constexpr int kPlane = LK * 16;             // operand plane: LK rows x 16 B (8 bf16)
-    static constexpr int kOp = 2 * 8 * kPlane;         // hi + lo, 8 planes = 64 channels
+    static constexpr int kTerms = BF ? 1 : 2;          // operand copies kept: hi (+ lo)
+    static constexpr int kOp = kTerms * 8 * kPlane;    // 8 planes = 64 channels, per copy
     static constexpr int kPP = LK / 8;                 // planes of a [LK x LK] pixel-pixel matrix (P, dS)
-    static constexpr int kP = 2 * kPP * kPlane;        // hi + lo
+    static constexpr int kP = kTerms * kPP * kPlane;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
@@ -81,12 +84,22 @@ __device__ __forceinline__ bool elect_one()
 
 // Converter: one staged slot ([LK px][64 ch] fp32 as two swizzled tiles) -> hi/lo operand planes
 // [8-channel chunk][pixel][16 B].  256 threads: thread t handles pixel (t & 127), octets 4*(t>>7)..+3.
-template <int LK>
+// bf16 I/O: the slot is one swizzled tile of 64 bf16 channels; the "conversion" is a de-swizzling copy into planes.
+template <int LK, bool BF = false>
 __device__ __forceinline__ void convert_slot(const uint8_t *slot, uint8_t *op, int t)
 {
-    using T = Tiles<LK>;
+    using T = Tiles<LK, BF>;
     const int r = t & 127, half = t >> 7;
     if (r >= LK) return;
+    if constexpr (BF) {
+        const uint8_t *src = slot + r * 128;
+        uint8_t *dh = op + r * 16 + half * 4 * T::kPlane;
+        const int sw = r & 7;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4 *>(dh + j * T::kPlane) = *reinterpret_cast<const uint4 *>(src + (((half * 4 + j) ^ sw) * 16));
+        return;
+    }
     const uint8_t *src = slot + r * 128 + half * T::kTile;      // octets 0-3 live in tile 0, 4-7 in tile 1
     uint8_t *dh = op + r * 16 + half * 4 * T::kPlane, *dl = dh + 8 * T::kPlane;
     const int sw = r & 7;
@@ -102,19 +115,23 @@ __device__ __forceinline__ void convert_slot(const uint8_t *slot, uint8_t *op, i
     }
 }
 
-// D (+)= A*B with the bf16x3 split: Ah*Bh + Ah*Bl + Al*Bh.  Executed by the whole (converged) MMA warp.
+// D (+)= A*B with the bf16x3 split: Ah*Bh + Ah*Bl + Al*Bh (TERMS = 3), or just Ah*Bh for bf16 I/O (TERMS = 1).
+// Executed by the whole (converged) MMA warp.
+template <int TERMS = 3>
 __device__ __forceinline__ void mma_split3(uint32_t d, uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl,
                                            uint32_t idesc, bool accumulate)
 {
     if (elect_one()) {
         mma_f16(d, ah, bh, idesc, accumulate);
-        mma_f16(d, ah, bl, idesc, true);
-        mma_f16(d, al, bh, idesc, true);
+        if constexpr (TERMS == 3) {
+            mma_f16(d, ah, bl, idesc, true);
+            mma_f16(d, al, bh, idesc, true);
+        }
     }
     __syncwarp();
 }
 // Same, for a whole K loop: NK k-steps, descriptors advance by (a_step, b_step) bytes per step.  One election.
-template <int NK>
+template <int NK, int TERMS = 3>
 __device__ __forceinline__ void mma_split3_loop(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t a_step, uint32_t a_lbo, uint32_t a_sbo,
                                                 uint32_t b_hi, uint32_t b_lo, uint32_t b_step, uint32_t b_lbo, uint32_t b_sbo,
                                                 uint32_t idesc, bool accumulate_first)
@@ -125,8 +142,10 @@ __device__ __forceinline__ void mma_split3_loop(uint32_t d, uint32_t a_hi, uint3
             const uint64_t ah = smem_desc(a_hi + ks * a_step, a_lbo, a_sbo), al = smem_desc(a_lo + ks * a_step, a_lbo, a_sbo);
             const uint64_t bh = smem_desc(b_hi + ks * b_step, b_lbo, b_sbo), bl = smem_desc(b_lo + ks * b_step, b_lbo, b_sbo);
             mma_f16(d, ah, bh, idesc, accumulate_first || ks > 0);
-            mma_f16(d, ah, bl, idesc, true);
-            mma_f16(d, al, bh, idesc, true);
+            if constexpr (TERMS == 3) {
+                mma_f16(d, ah, bl, idesc, true);
+                mma_f16(d, al, bh, idesc, true);
+            }
         }
     }
     __syncwarp();
@@ -154,16 +173,17 @@ inline EncodeFn get_encode()
     });
     return fn;
 }
-// NHWC fp32 tensor [B,H,W,C]; box = [32 ch] x [LK pixels along W (row pass) or along H (column pass)]
-inline bool make_map(CUtensorMap *m, const void *base, int B, int H, int W, int C, int LK, bool col)
+// NHWC tensor [B,H,W,C] (fp32 or bf16); box = [128 bytes of channels] x [LK pixels along W (row pass) or H (column pass)]
+inline bool make_map(CUtensorMap *m, const void *base, int B, int H, int W, int C, int LK, bool col, bool bf16 = false)
 {
     EncodeFn enc = get_encode();
     if (!enc) return false;
+    const cuuint64_t es_bytes = bf16 ? 2 : 4;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-    cuuint32_t box[4] = {32, col ? 1u : (cuuint32_t)LK, col ? (cuuint32_t)LK : 1u, 1};
+    cuuint64_t strides[3] = {(cuuint64_t)C * es_bytes, (cuuint64_t)W * C * es_bytes, (cuuint64_t)H * W * C * es_bytes};
+    cuuint32_t box[4] = {bf16 ? 64u : 32u, col ? 1u : (cuuint32_t)LK, col ? (cuuint32_t)LK : 1u, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(base), dims, strides, box, es,
+    return enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(base), dims, strides, box, es,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -180,7 +200,7 @@ inline int sm_count()
 }
 inline bool shape_supported(Dims d, int dtype)
 {
-    if (dtype != CCA_F32) return false;
+    if (dtype != CCA_F32 && dtype != CCA_BF16) return false;
     if (d.Cq % 16 != 0 || d.Cq > 64 || d.Cq < 16 || d.C % kNC != 0) return false;
     if (lk_for(d.H) == 0 || lk_for(d.W) == 0) return false;
     return get_encode() != nullptr;

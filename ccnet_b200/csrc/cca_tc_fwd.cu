@@ -86,8 +86,8 @@ __device__ __forceinline__ Item decode_item(const FwdParams &p, int idx)
         if (p.dbg && blockIdx.x == 0 && dbg_n < 512) p.dbg[(role) * 512 + dbg_n++] = clock64();  \
     } while (0)
 
-template <int LK> struct FwdSmem {
-    using T = Tiles<LK>;
+template <int LK, bool BF> struct FwdSmem {
+    using T = Tiles<LK, BF>;
     static constexpr int off_ld = 0;                          // kNLd load slots
     static constexpr int off_out = off_ld + kNLd * T::kSlot;  // kNOut out slots
     static constexpr int off_op = off_out + kNOut * T::kSlot; // 2 operand buffers
@@ -117,15 +117,16 @@ __device__ __forceinline__ void wait_done(const unsigned int *cnt, unsigned int 
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-template <int LK>
+template <int LK, bool BF>
 __global__ void __launch_bounds__(kThreads, 1)
 cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant__ CUtensorMap mqr,
                   const __grid_constant__ CUtensorMap mkc, const __grid_constant__ CUtensorMap mkr,
                   const __grid_constant__ CUtensorMap mvc, const __grid_constant__ CUtensorMap mvr,
                   const __grid_constant__ CUtensorMap moc, const __grid_constant__ CUtensorMap mor, FwdParams p)
 {
-    using T = Tiles<LK>;
-    using S = FwdSmem<LK>;
+    using T = Tiles<LK, BF>;
+    using S = FwdSmem<LK, BF>;
+    constexpr int TERMS = BF ? 1 : 3;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S::off_bar);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::off_bar + 8 * B_COUNT);
@@ -175,7 +176,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                     uint8_t *dst = smem + S::off_ld + slot * T::kSlot;
                     mbar_expect_tx(&bars[B_LD_FULL + slot], T::kSlot);
                     tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, it.b);
-                    tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, it.b);
+                    if constexpr (!BF) tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, it.b);
                     ++g;
                 };
                 Item cur = item_of(0);
@@ -206,9 +207,9 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                 CCA_STAMP(2);
                 for (int ks = 0; ks < KQ; ++ks) {
                     const uint32_t ao = ks * 2 * T::kPlane;
-                    mma_split3(tmem, smem_desc(qb + ao, T::kPlane, 128), smem_desc(qb + 8 * T::kPlane + ao, T::kPlane, 128),
-                               smem_desc(kb + ao, T::kPlane, 128), smem_desc(kb + 8 * T::kPlane + ao, T::kPlane, 128),
-                               idesc_s, ks > 0);
+                    mma_split3<TERMS>(tmem, smem_desc(qb + ao, T::kPlane, 128), smem_desc(qb + 8 * T::kPlane + ao, T::kPlane, 128),
+                                      smem_desc(kb + ao, T::kPlane, 128), smem_desc(kb + 8 * T::kPlane + ao, T::kPlane, 128),
+                                      idesc_s, ks > 0);
                 }
                 commit_to(&bars[B_S_FULL]);
                 commit_to(&bars[B_OP_EMPTY + (u & 1)]);
@@ -238,8 +239,10 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                             const uint64_t vh = smem_desc(vb + ks * 256, 128, T::kPlane);
                             const uint64_t vl = smem_desc(vb + 8 * T::kPlane + ks * 256, 128, T::kPlane);
                             mma_f16_ts(d, ph, vh, idesc_o, ks > 0);
-                            mma_f16_ts(d, ph, vl, idesc_o, true);
-                            mma_f16_ts(d, pl, vh, idesc_o, true);
+                            if constexpr (TERMS == 3) {
+                                mma_f16_ts(d, ph, vl, idesc_o, true);
+                                mma_f16_ts(d, pl, vh, idesc_o, true);
+                            }
                         }
                     }
                     __syncwarp();
@@ -276,7 +279,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                     uint8_t *dst = smem + S::off_out + os * T::kSlot;
                     mbar_expect_tx(&bars[B_OUT_FULL + os], T::kSlot);
                     tma_load_4d(dst, &mor, &bars[B_OUT_FULL + os], n * kNC, 0, it.i, it.b);
-                    tma_load_4d(dst + T::kTile, &mor, &bars[B_OUT_FULL + os], n * kNC + 32, 0, it.i, it.b);
+                    if constexpr (!BF) tma_load_4d(dst + T::kTile, &mor, &bars[B_OUT_FULL + os], n * kNC + 32, 0, it.i, it.b);
                 };
                 while (prep < total_chunks && prep < 2 && can_prepare(prep)) { prepare(prep); ++prep; }
                 for (uint32_t c = 0; c < total_chunks; ++c) {
@@ -287,7 +290,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                     const CUtensorMap *mo = it.col ? &moc : &mor;
                     const int cw = it.col ? it.i : 0, ch = it.col ? 0 : it.i;
                     tma_store_4d(mo, slot, n * kNC, cw, ch, it.b);
-                    tma_store_4d(mo, slot + T::kTile, n * kNC + 32, cw, ch, it.b);
+                    if constexpr (!BF) tma_store_4d(mo, slot + T::kTile, n * kNC + 32, cw, ch, it.b);
                     tma_store_commit();
                     if (n == NCH - 1) {
                         if (it.col && p.mode == MODE_FUSED) {
@@ -321,7 +324,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             CCA_STAMP(1);
             mbar_wait(&bars[B_OP_EMPTY + ob], ((g >> 1) & 1) ^ 1);
             CCA_STAMP(1);
-            convert_slot<LK>(smem + S::off_ld + slot * T::kSlot, smem + S::off_op + ob * T::kOp, t);
+            convert_slot<LK, BF>(smem + S::off_ld + slot * T::kSlot, smem + S::off_op + ob * T::kOp, t);
             fence_proxy_async();
             mbar_arrive(&bars[B_OP_FULL + ob]);
             mbar_arrive(&bars[B_LD_EMPTY + slot]);
@@ -387,9 +390,12 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             for (int c0 = 0; c0 < LK / 2; c0 += 8) {
                 uint32_t hi[8], lo[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) split2(s[2 * (c0 + e)], s[2 * (c0 + e) + 1], hi[e], lo[e]);
+                for (int e = 0; e < 8; ++e) {
+                    if constexpr (BF) hi[e] = pack_bf16(s[2 * (c0 + e)], s[2 * (c0 + e) + 1]);
+                    else split2(s[2 * (c0 + e)], s[2 * (c0 + e) + 1], hi[e], lo[e]);
+                }
                 tmem_st8(pdst + c0, hi);
-                tmem_st8(pdst + LK / 2 + c0, lo);
+                if constexpr (!BF) tmem_st8(pdst + LK / 2 + c0, lo);
             }
             tmem_st_wait();
             tc_fence_before();
@@ -432,7 +438,26 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                 if (r < it.L) {                                          // rows >= L are clipped by the TMA store
                     uint8_t *row = slot + r * 128;
                     const int sw = r & 7;
-                    if (it.col) {
+                    if constexpr (BF) {
+                        // bf16 staging tile: one 128-byte row = 64 channels = 8 chunks of 8 bf16
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            uint4 *dst = reinterpret_cast<uint4 *>(row + ((j ^ sw) * 16));
+                            float v[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[e] = o[8 * j + e] * sa;
+                            if (!it.col) {
+                                const uint4 q = *dst;
+                                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    v[2 * e] = fmaf(bf_lo(w[e]), sb, v[2 * e]);
+                                    v[2 * e + 1] = fmaf(bf_hi(w[e]), sb, v[2 * e + 1]);
+                                }
+                            }
+                            *dst = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                        }
+                    } else if (it.col) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {                   // 16 chunks of 4 channels
                             float4 *dst = reinterpret_cast<float4 *>(row + (j >> 3) * T::kTile + (((j & 7) ^ sw) * 16));
@@ -470,7 +495,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
 
 long long *g_dbg = nullptr;   // set through cca_b200__set_debug_buffer (profiling aid, not part of the ABI)
 
-template <int LK>
+template <int LK, bool BF>
 cudaError_t launch_fwd(const void *q, const void *k, const void *v, void *out, float *lse, float2 *stats, unsigned int *done,
                        Dims d, int mode, cudaStream_t st, const char **why)
 {
@@ -479,7 +504,7 @@ cudaError_t launch_fwd(const void *q, const void *k, const void *v, void *out, f
     const int ch[4] = {d.Cq, d.Cq, d.C, d.C};
     for (int t = 0; t < 4; ++t)
         for (int r = 0; r < 2; ++r)
-            if (!make_map(&m[2 * t + r], base[t], d.B, d.H, d.W, ch[t], LK, r == 0)) {
+            if (!make_map(&m[2 * t + r], base[t], d.B, d.H, d.W, ch[t], LK, r == 0, BF)) {
                 if (why) *why = "cuTensorMapEncodeTiled failed";
                 return cudaErrorInvalidValue;
             }
@@ -487,12 +512,12 @@ cudaError_t launch_fwd(const void *q, const void *k, const void *v, void *out, f
     p.B = d.B; p.H = d.H; p.W = d.W; p.C = d.C; p.Cq = d.Cq;
     p.mode = mode; p.stats = stats; p.lse = lse; p.done = done;
     p.dbg = g_dbg ? g_dbg + (mode == MODE_ROW_ONLY ? 2560 : 0) : nullptr;
-    auto kern = cca_tc_fwd_kernel<LK>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem<LK>::kBytes);
+    auto kern = cca_tc_fwd_kernel<LK, BF>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem<LK, BF>::kBytes);
     if (e != cudaSuccess) return e;
     const int items = mode == MODE_FUSED ? d.B * (d.W + d.H) : (mode == MODE_COL_ONLY ? d.B * d.W : d.B * d.H);
     const int grid = items < sm_count() ? items : sm_count();
-    kern<<<grid, kThreads, FwdSmem<LK>::kBytes, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], p);
+    kern<<<grid, kThreads, FwdSmem<LK, BF>::kBytes, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], p);
     count_launch();
     return cudaGetLastError();
 }
@@ -517,25 +542,36 @@ void set_tc_two_pass(int on) { g_fused = on ? 0 : 1; }
 
 bool tc_forward_supported(Dims d, int dtype) { return tc::shape_supported(d, dtype); }
 
-// q,k,v,out are channels-last (NHWC) fp32.  ws: [B*H*W] float2 stats, then [B] unsigned counters.
+// q,k,v,out are channels-last (NHWC), fp32 or bf16.  ws: [B*H*W] float2 stats, then [B] unsigned counters.
+namespace {
+template <bool BF>
+cudaError_t launch_fwd_lk(int lk, const void *q, const void *k, const void *v, void *out, float *lse, float2 *stats,
+                          unsigned int *done, Dims d, int mode, cudaStream_t st, const char **why)
+{
+    return lk == 80 ? launch_fwd<80, BF>(q, k, v, out, lse, stats, done, d, mode, st, why)
+                    : launch_fwd<112, BF>(q, k, v, out, lse, stats, done, d, mode, st, why);
+}
+}  // namespace
+
 cudaError_t tc_forward(const void *q, const void *k, const void *v, void *out, float *lse, void *ws, Dims d, int dtype,
                        cudaStream_t st, const char **why)
 {
-    (void)dtype;
     float2 *stats = reinterpret_cast<float2 *>(ws);
     unsigned int *done = reinterpret_cast<unsigned int *>(stats + (size_t)d.B * d.H * d.W);
     const int lkc = lk_for(d.H), lkr = lk_for(d.W);
+    const bool bf = dtype == CCA_BF16;
+    auto go = [&](int lk, int mode) {
+        return bf ? launch_fwd_lk<true>(lk, q, k, v, out, lse, stats, done, d, mode, st, why)
+                  : launch_fwd_lk<false>(lk, q, k, v, out, lse, stats, done, d, mode, st, why);
+    };
     if (lkc == lkr && use_fused()) {
         cudaError_t e = cudaMemsetAsync(done, 0, sizeof(unsigned int) * d.B, st);
         if (e != cudaSuccess) return e;
-        return lkc == 80 ? launch_fwd<80>(q, k, v, out, lse, stats, done, d, MODE_FUSED, st, why)
-                         : launch_fwd<112>(q, k, v, out, lse, stats, done, d, MODE_FUSED, st, why);
+        return go(lkc, MODE_FUSED);
     }
-    cudaError_t e = lkc == 80 ? launch_fwd<80>(q, k, v, out, lse, stats, done, d, MODE_COL_ONLY, st, why)
-                              : launch_fwd<112>(q, k, v, out, lse, stats, done, d, MODE_COL_ONLY, st, why);
+    cudaError_t e = go(lkc, MODE_COL_ONLY);
     if (e != cudaSuccess) return e;
-    return lkr == 80 ? launch_fwd<80>(q, k, v, out, lse, stats, done, d, MODE_ROW_ONLY, st, why)
-                     : launch_fwd<112>(q, k, v, out, lse, stats, done, d, MODE_ROW_ONLY, st, why);
+    return go(lkr, MODE_ROW_ONLY);
 }
 
 }  // namespace cca

@@ -121,6 +121,29 @@ def test_backward_tensor_core_vs_oracle(shape):
         assert (got - ref).abs().max().item() <= FP32_TOL * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 256, 20, 97), (1, 64, 64, 112, 80), (3, 16, 64, 1, 5), (2, 64, 512, 33, 47), (2, 64, 512, 97, 97)])
+def test_bf16_tensor_core_forward_backward_vs_oracle(shape):
+    """bf16 I/O on the tcgen05 kernels (single-term MMAs, bf16 staging / TMA reduce-add): against the fp64 oracle
+    evaluated on the bf16-rounded inputs, tolerance 1e-2 (forward) / 3e-2 (gradients), relative to max|ref|."""
+    from ccnet_b200 import cca_backward, cca_forward
+    O = _oracle()
+    dev = _dev()
+    q, k, v = _rand_qkv(*shape, seed=41 + sum(shape), scale=0.6, dtype=torch.bfloat16)
+    dout = torch.randn(v.shape, generator=torch.Generator().manual_seed(9)).to(torch.bfloat16)
+    qd, kd, vd, dd = q.to(dev), k.to(dev), v.to(dev), dout.to(dev)
+    out, lse = cca_forward(qd, kd, vd, impl="tc")
+    assert out.dtype == torch.bfloat16 and lse.dtype == torch.float32
+    ro, rl = O.cca_forward(q.double(), k.double(), v.double())
+    assert (out.cpu().double() - ro).abs().max().item() <= BF16_TOL * max(1.0, ro.abs().max().item())
+    assert (lse.cpu().double() - rl).abs().max().item() <= BF16_TOL
+    dq, dk, dv = cca_backward(dd, qd, kd, vd, out, lse, impl="tc")
+    rq, rk, rv = O.cca_backward(dout.double(), q.double(), k.double(), v.double())
+    for got, ref, name in ((dq, rq, "dq"), (dk, rk, "dk"), (dv, rv, "dv")):
+        assert got.dtype == torch.bfloat16
+        err = (got.cpu().double() - ref).abs().max().item()
+        assert err <= 3 * BF16_TOL * max(1.0, ref.abs().max().item()), (name, err)
+
+
 def test_forward_fused_launch_matches_two_launch_mode():
     """The single fused launch (per-sample column->row scheduling with completion counters) and the two-launch mode
     must give bit-identical results; run both a few times to shake out scheduling races."""
