@@ -325,6 +325,25 @@ def run_ours(args):
                 "op_layout": op_layout,
                 "timing": "CUDA events on torch's current stream (the launching stream), L2 flushed between iterations"}
 
+    # ---- the same op in the other I/O dtype (BASELINE config 2: "fp32 vs bf16"), operator-only ---------------------------
+    other = None
+    if rank == 0:
+        odt = torch.bfloat16 if dtype == torch.float32 else torch.float32
+        oes = 2 if odt == torch.bfloat16 else 4
+        fmt = torch.channels_last if tc_eligible(B, Cq, C, H, W, odt) and args.kernels != "simt" else torch.contiguous_format
+        q2, k2, v2, do2 = (t.to(odt).contiguous(memory_format=fmt) for t in (q, k, v, do))
+        out2, lse2 = cca_forward(q2, k2, v2, impl=args.kernels)
+        f2, _ = op_time(lambda: cca_forward(q2, k2, v2, impl=args.kernels), iters=6)
+        b2, _ = op_time(lambda: cca_backward(do2, q2, k2, v2, out2, lse2, impl=args.kernels), iters=6)
+        bf2, bb2 = alg_bytes(B, C, H, W, oes, True, False), alg_bytes(B, C, H, W, oes, False, True)
+        other = {"dtype": "bf16" if odt == torch.bfloat16 else "f32",
+                 "op_fwd": {"ms": f2, "alg_bytes": bf2, "gbs": bf2 / f2 / 1e6, "frac": bf2 / f2 / 1e6 / peak},
+                 "op_bwd": {"ms": b2, "alg_bytes": bb2, "gbs": bb2 / b2 / 1e6, "frac": bb2 / b2 / 1e6 / peak},
+                 "op_fwd_bwd_pixels_per_s_R2": B * H * W / (R * (f2 + b2) * 1e-3),
+                 "layout": "channels_last" if fmt == torch.channels_last else "nchw"}
+        del q2, k2, v2, do2, out2, lse2
+    roofline["other_dtype"] = other
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         r = cpu_reference_run(3, 1)
