@@ -45,19 +45,20 @@ constexpr int kNOp = 3;             // rotating operand buffers
 
 template <int LK, bool BF> struct BwdSmem {
     using T = Tiles<LK, BF>;
-    static constexpr int off_ld = 0;                       // 2 load slots
-    static constexpr int off_out = off_ld + 2 * T::kSlot;  // 1 out slot (the epilogue has slack; the store warp drives it)
-    static constexpr int off_p = off_out + T::kSlot;       // P / dS planes (hi, lo); over-reads land in the operand buffers
-    static constexpr int off_op = off_p + T::kP;           // kNOp operand buffers
-    static constexpr int off_tail = off_op + kNOp * T::kOp;// pad: an M=128 MMA reads (128 - LK) rows past the last plane
+    static constexpr int kNLd = BF ? 6 : 2;                // bf16 tiles are consumed by UMMA in place: deeper ring, no operand buffers
+    static constexpr int off_ld = 0;                       // kNLd load slots
+    static constexpr int off_out = off_ld + kNLd * T::kSlot; // 1 out slot (the epilogue has slack; the store warp drives it)
+    static constexpr int off_p = off_out + T::kSlot;       // P / dS planes (hi, lo); over-reads land in the operand buffers / pad
+    static constexpr int off_op = off_p + T::kP;           // kNOp operand buffers (fp32 only)
+    static constexpr int off_tail = off_op + (BF ? (16 - LK / 8) * T::kPlane : kNOp * T::kOp); // bf16: pad for the P^T over-read (16 planes)
     static constexpr int off_bar = off_tail + (128 - LK) * 16 + 256;
     static constexpr int kBytes = off_bar + 320;
     static_assert(kBytes <= 232448, "shared memory budget");
 };
 
-enum { B_LD_FULL = 0, B_LD_EMPTY = 2, B_OP_FULL = 4, B_OP_EMPTY = 7, B_S_FULL = 10, B_S_EMPTY = 12, B_P_FULL = 14,
-       B_P_EMPTY = 15, B_O_FULL = 16, B_O_EMPTY = 18, B_OUT_FULL = 20, B_STAGED = 21, B_DP_FULL = 22, B_DS_FULL = 23,
-       B_COUNT = 24 };
+enum { B_LD_FULL = 0, B_LD_EMPTY = 6, B_OP_FULL = 12, B_OP_EMPTY = 15, B_S_FULL = 18, B_S_EMPTY = 20, B_P_FULL = 22,
+       B_P_EMPTY = 23, B_O_FULL = 24, B_O_EMPTY = 26, B_OUT_FULL = 28, B_STAGED = 29, B_DP_FULL = 30, B_DS_FULL = 31,
+       B_COUNT = 32 };
 
 // Per line the ring carries  Q K (V_n dO_n)* Q K ; item g is converted into operand buffer g % 3, so the conversion of
 // the next chunk overlaps the MMAs of the current one.  MMAs per line: S (phase A), per chunk dP += dO V^T then
@@ -73,6 +74,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
     using T = Tiles<LK, BF>;
     using S = BwdSmem<LK, BF>;
     constexpr int TERMS = BF ? 1 : 3;
+    constexpr int kNLd = S::kNLd;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S::off_bar);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::off_bar + 8 * B_COUNT);
@@ -85,10 +87,8 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
     const int nk = (total_lines - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&bars[B_LD_FULL + i], 1);            mbar_init(&bars[B_LD_EMPTY + i], kConvThreads);
-            mbar_init(&bars[B_O_FULL + i], 1);             mbar_init(&bars[B_O_EMPTY + i], 128);
-        }
+        for (int i = 0; i < kNLd; ++i) { mbar_init(&bars[B_LD_FULL + i], 1); mbar_init(&bars[B_LD_EMPTY + i], BF ? 1 : kConvThreads); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_O_FULL + i], 1); mbar_init(&bars[B_O_EMPTY + i], 128); }
         for (int i = 0; i < kNOp; ++i) { mbar_init(&bars[B_OP_FULL + i], kConvThreads); mbar_init(&bars[B_OP_EMPTY + i], 1); }
         mbar_init(&bars[B_OUT_FULL], 1); mbar_init(&bars[B_STAGED], 128);
         for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_S_FULL + i], 1); mbar_init(&bars[B_S_EMPTY + i], 128); }
@@ -124,8 +124,8 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                 auto emit = [&](const CUtensorMap *m, int c0, int line) {
                     int cw, ch, cb;
                     line_coords(line, cw, ch, cb);
-                    const int slot = g & 1;
-                    mbar_wait(&bars[B_LD_EMPTY + slot], ((g >> 1) & 1) ^ 1);
+                    const int slot = g % kNLd;
+                    mbar_wait(&bars[B_LD_EMPTY + slot], ((g / kNLd) & 1) ^ 1);
                     CCA_STAMP(0);
                     uint8_t *dst = smem + S::off_ld + slot * T::kSlot;
                     mbar_expect_tx(&bars[B_LD_FULL + slot], T::kSlot);
@@ -153,9 +153,24 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
             const uint32_t LO8 = 8 * T::kPlane, LOP = T::kPP * T::kPlane;
             uint32_t u = 0, oc = 0;
             int dbg_n = lane == 0 ? 0 : 512;
-            auto opb = [&](uint32_t g) { return op_base + (g % kNOp) * T::kOp; };
-            auto wait_op = [&](uint32_t g) { mbar_wait(&bars[B_OP_FULL + g % kNOp], (g / kNOp) & 1); };
-            auto free_op = [&](uint32_t g) { commit_to(&bars[B_OP_EMPTY + g % kNOp]); };
+            // operand sources: fp32 -> converted planes (item g -> operand buffer g % 3, K-major / MN-major by descriptor);
+            //                  bf16 -> the TMA tile of item g itself (load slot g % kNLd) read with SWIZZLE_128B descriptors:
+            //                          K-major use: k-step = +32 B; MN-major use: k-step = +2048 B (16 pixel rows)
+            const uint32_t ld_base = smem_u32(smem + S::off_ld);
+            auto opb = [&](uint32_t g) { return BF ? ld_base + (g % kNLd) * T::kSlot : op_base + (g % kNOp) * T::kOp; };
+            auto wait_op = [&](uint32_t g) {
+                if constexpr (BF) mbar_wait(&bars[B_LD_FULL + g % kNLd], (g / kNLd) & 1);
+                else mbar_wait(&bars[B_OP_FULL + g % kNOp], (g / kNOp) & 1);
+            };
+            auto free_op = [&](uint32_t g) {
+                if constexpr (BF) commit_to(&bars[B_LD_EMPTY + g % kNLd]);
+                else commit_to(&bars[B_OP_EMPTY + g % kNOp]);
+            };
+            // channel-tile operand parameters: (k-step, lbo, sbo, layout) when the contraction runs over channels (kmaj) or
+            // over pixels (mnmaj)
+            constexpr uint32_t KS_K = BF ? 32 : 2 * T::kPlane, LBO_K = BF ? 16 : T::kPlane, SBO_K = BF ? 1024 : 128;
+            constexpr uint32_t KS_MN = BF ? 2048 : 256, LBO_MN = BF ? 16 : 128, SBO_MN = BF ? 1024 : T::kPlane;
+            constexpr uint32_t LAY = BF ? kSw128 : 0;
             auto issue_s = [&](int k) {                       // S(k) = Q K^T into S buffer k&1
                 const uint32_t q = opb(u), kk = opb(u + 1);
                 wait_op(u); wait_op(u + 1);
@@ -163,9 +178,9 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                 tc_fence_after();
                 const uint32_t d = tmem + (k & 1) * 128;
                 for (int ks = 0; ks < KQ; ++ks) {
-                    const uint32_t ao = ks * 2 * T::kPlane;
-                    mma_split3<TERMS>(d, smem_desc(q + ao, T::kPlane, 128), smem_desc(q + LO8 + ao, T::kPlane, 128),
-                                      smem_desc(kk + ao, T::kPlane, 128), smem_desc(kk + LO8 + ao, T::kPlane, 128), id_kk_s, ks > 0);
+                    const uint32_t ao = ks * KS_K;
+                    mma_split3<TERMS>(d, smem_desc(q + ao, LBO_K, SBO_K, LAY), smem_desc(q + LO8 + ao, LBO_K, SBO_K, LAY),
+                                      smem_desc(kk + ao, LBO_K, SBO_K, LAY), smem_desc(kk + LO8 + ao, LBO_K, SBO_K, LAY), id_kk_s, ks > 0);
                 }
                 commit_to(&bars[B_S_FULL + (k & 1)]);
                 free_op(u); free_op(u + 1);
@@ -182,13 +197,13 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                     const uint32_t vb = opb(u), db = opb(u + 1);
                     wait_op(u); wait_op(u + 1);
                     tc_fence_after();
-                    mma_split3_loop<kNC / 16, TERMS>(sdp, db, db + LO8, 2 * T::kPlane, T::kPlane, 128,
-                                              vb, vb + LO8, 2 * T::kPlane, T::kPlane, 128, id_kk_s, n > 0);
+                    mma_split3_loop<kNC / 16, TERMS>(sdp, db, db + LO8, KS_K, LBO_K, SBO_K,
+                                                     vb, vb + LO8, KS_K, LBO_K, SBO_K, id_kk_s, n > 0, LAY, LAY);
                     free_op(u);                                   // V is only needed by dP
                     mbar_wait(&bars[B_O_EMPTY + (oc & 1)], ((oc >> 1) & 1) ^ 1);
                     tc_fence_after();
                     mma_split3_loop<LK / 16, TERMS>(tmem + kTmemO + (oc & 1) * kNC, pb, pb + LOP, 256, 128, T::kPlane,
-                                             db, db + LO8, 256, 128, T::kPlane, id_mn_mn, false);
+                                                    db, db + LO8, KS_MN, LBO_MN, SBO_MN, id_mn_mn, false, 0, LAY);
                     commit_to(&bars[B_O_FULL + (oc & 1)]);
                     free_op(u + 1);
                     CCA_STAMP(2);
@@ -204,14 +219,14 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                     mbar_wait(&bars[B_O_EMPTY + (oc & 1)], ((oc >> 1) & 1) ^ 1);
                     tc_fence_after();
                     mma_split3_loop<LK / 16, TERMS>(tmem + kTmemO + (oc & 1) * kNC, pb, pb + LOP, 2 * T::kPlane, T::kPlane, 128,
-                                             kk, kk + LO8, 256, 128, T::kPlane, id_k_mn, false);
+                                                    kk, kk + LO8, KS_MN, LBO_MN, SBO_MN, id_k_mn, false, 0, LAY);
                     commit_to(&bars[B_O_FULL + (oc & 1)]);
                     free_op(u + 1);
                     ++oc;
                     mbar_wait(&bars[B_O_EMPTY + (oc & 1)], ((oc >> 1) & 1) ^ 1);
                     tc_fence_after();
                     mma_split3_loop<LK / 16, TERMS>(tmem + kTmemO + (oc & 1) * kNC, pb, pb + LOP, 256, 128, T::kPlane,
-                                             q, q + LO8, 256, 128, T::kPlane, id_mn_mn, false);
+                                                    q, q + LO8, KS_MN, LBO_MN, SBO_MN, id_mn_mn, false, 0, LAY);
                     commit_to(&bars[B_O_FULL + (oc & 1)]);
                     free_op(u);
                     ++oc;
@@ -249,11 +264,11 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
         // =============================== converters (256 threads) ===============================
         reg_dec<kRegsConv>();
         const int t = tid - kWarpConv0 * 32;
-        const uint32_t total = (uint32_t)nk * NI;
+        const uint32_t total = BF ? 0u : (uint32_t)nk * NI;         // bf16 tiles need no conversion
         int dbg_n = t == 0 ? 0 : 512;
         for (uint32_t g = 0; g < total; ++g) {
-            const int slot = g & 1, ob = g % kNOp;
-            mbar_wait(&bars[B_LD_FULL + slot], (g >> 1) & 1);
+            const int slot = g % kNLd, ob = g % kNOp;
+            mbar_wait(&bars[B_LD_FULL + slot], (g / kNLd) & 1);
             CCA_STAMP(1);
             mbar_wait(&bars[B_OP_EMPTY + ob], ((g / kNOp) & 1) ^ 1);
             CCA_STAMP(1);

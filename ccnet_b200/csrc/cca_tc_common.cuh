@@ -10,6 +10,8 @@ namespace tc {
 using namespace sm100;
 
 constexpr int kNC = 64;   // channels per chunk (one ring slot = [LK px][64 ch] fp32 = two swizzled TMA tiles)
+constexpr uint32_t kSw128 = 2;   // UMMA smem-descriptor layout type SWIZZLE_128B: a bf16 TMA tile [rows][128 B] is directly a
+                                 // K-major operand (rows = M/N, k-step = +32 B) or an MN-major one (rows = K, k-step = +2048 B)
 
 // Thread layout of both kernels (five warpgroups, registers rebalanced with setmaxnreg):
 //   warps 0-3   (128 thr) : epilogue group        (TMEM lane == pixel; accumulators -> staging -> TMA store)
@@ -134,13 +136,13 @@ __device__ __forceinline__ void mma_split3(uint32_t d, uint64_t ah, uint64_t al,
 template <int NK, int TERMS = 3>
 __device__ __forceinline__ void mma_split3_loop(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t a_step, uint32_t a_lbo, uint32_t a_sbo,
                                                 uint32_t b_hi, uint32_t b_lo, uint32_t b_step, uint32_t b_lbo, uint32_t b_sbo,
-                                                uint32_t idesc, bool accumulate_first)
+                                                uint32_t idesc, bool accumulate_first, uint32_t a_layout = 0, uint32_t b_layout = 0)
 {
     if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < NK; ++ks) {
-            const uint64_t ah = smem_desc(a_hi + ks * a_step, a_lbo, a_sbo), al = smem_desc(a_lo + ks * a_step, a_lbo, a_sbo);
-            const uint64_t bh = smem_desc(b_hi + ks * b_step, b_lbo, b_sbo), bl = smem_desc(b_lo + ks * b_step, b_lbo, b_sbo);
+            const uint64_t ah = smem_desc(a_hi + ks * a_step, a_lbo, a_sbo, a_layout), al = smem_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_layout);
+            const uint64_t bh = smem_desc(b_hi + ks * b_step, b_lbo, b_sbo, b_layout), bl = smem_desc(b_lo + ks * b_step, b_lbo, b_sbo, b_layout);
             mma_f16(d, ah, bh, idesc, accumulate_first || ks > 0);
             if constexpr (TERMS == 3) {
                 mma_f16(d, ah, bl, idesc, true);

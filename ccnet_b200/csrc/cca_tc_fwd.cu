@@ -37,7 +37,8 @@ constexpr int kTmemCols = 512;      // S [0,128)   P double buffer (hi/lo) [128,
 constexpr int kTmemP = 128, kTmemO = 384, kNOB = 2;
 constexpr int kRegsSoft = 168, kRegsEpi = 128;
 static_assert(reg_pool_ok(kRegsSoft, kRegsEpi), "setmaxnreg pool");
-constexpr int kNLd = 3, kNOut = 3;  // ring depths (smem slots)
+constexpr int kNOut = 3;            // staging slots
+constexpr int kNLdMax = 6;          // load ring: 3 slots (fp32: 28 KB each) or 6 (bf16: 14 KB each, consumed by UMMA in place)
 
 enum { MODE_FUSED = 0, MODE_COL_ONLY = 2, MODE_ROW_ONLY = 3 };
 
@@ -88,18 +89,19 @@ __device__ __forceinline__ Item decode_item(const FwdParams &p, int idx)
 
 template <int LK, bool BF> struct FwdSmem {
     using T = Tiles<LK, BF>;
+    static constexpr int kNLd = BF ? 6 : 3;
     static constexpr int off_ld = 0;                          // kNLd load slots
     static constexpr int off_out = off_ld + kNLd * T::kSlot;  // kNOut out slots
-    static constexpr int off_op = off_out + kNOut * T::kSlot; // 2 operand buffers
-    static constexpr int off_tail = off_op + 2 * T::kOp;      // pad: an M=128 MMA reads (128 - LK) rows past the last plane
+    static constexpr int off_op = off_out + kNOut * T::kSlot; // 2 operand buffers (fp32 only: bf16 tiles are UMMA operands as loaded)
+    static constexpr int off_tail = off_op + (BF ? 0 : 2 * T::kOp); // pad: an M=128 MMA reads (128 - LK) rows past the last plane
     static constexpr int off_scale = off_tail + (128 - LK) * 16;          // float2 (sa, sb) [2][128]: softmax group -> epilogue group
     static constexpr int off_bar = off_scale + 2 * 128 * 8;
-    static constexpr int kBytes = off_bar + 320;
+    static constexpr int kBytes = off_bar + 384;
     static_assert(kBytes <= 232448, "shared memory budget");
 };
 
-enum { B_LD_FULL = 0, B_LD_EMPTY = 3, B_OP_FULL = 6, B_OP_EMPTY = 8, B_S_FULL = 10, B_S_EMPTY = 11, B_P_FULL = 12,
-       B_P_EMPTY = 14, B_O_FULL = 16, B_O_EMPTY = 18, B_OUT_FULL = 20, B_SC_EMPTY = 23, B_SC_FULL = 25, B_STAGED = 27, B_COUNT = 30 };
+enum { B_LD_FULL = 0, B_LD_EMPTY = 6, B_OP_FULL = 12, B_OP_EMPTY = 14, B_S_FULL = 16, B_S_EMPTY = 17, B_P_FULL = 18,
+       B_P_EMPTY = 20, B_O_FULL = 22, B_O_EMPTY = 24, B_OUT_FULL = 26, B_SC_EMPTY = 29, B_SC_FULL = 31, B_STAGED = 33, B_COUNT = 36 };
 
 __device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p)
 {
@@ -127,6 +129,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
     using T = Tiles<LK, BF>;
     using S = FwdSmem<LK, BF>;
     constexpr int TERMS = BF ? 1 : 3;
+    constexpr int kNLd = S::kNLd;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S::off_bar);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::off_bar + 8 * B_COUNT);
@@ -141,7 +144,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
     const int qkpos = NCH >= 3 ? 2 : NCH - 1;
 
     if (tid == 0) {
-        for (int i = 0; i < kNLd; ++i) { mbar_init(&bars[B_LD_FULL + i], 1); mbar_init(&bars[B_LD_EMPTY + i], kConvThreads); }
+        for (int i = 0; i < kNLd; ++i) { mbar_init(&bars[B_LD_FULL + i], 1); mbar_init(&bars[B_LD_EMPTY + i], BF ? 1 : kConvThreads); }
         for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_OP_FULL + i], kConvThreads); mbar_init(&bars[B_OP_EMPTY + i], 1); }
         for (int i = 0; i < kNOB; ++i) { mbar_init(&bars[B_O_FULL + i], 1); mbar_init(&bars[B_O_EMPTY + i], 128); }
         for (int i = 0; i < kNOut; ++i) { mbar_init(&bars[B_OUT_FULL + i], 1); mbar_init(&bars[B_STAGED + i], 128); }
@@ -198,22 +201,37 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             const uint32_t op_base = smem_u32(smem + S::off_op);
             uint32_t u = 0, oc = 0;
             int dbg_n = lane == 0 ? 0 : 512;
-            auto issue_s = [&](int k) {            // S(k) = Q K^T, Q in operand buffer u&1, K in (u+1)&1
-                const uint32_t qb = op_base + (u & 1) * T::kOp, kb = op_base + ((u + 1) & 1) * T::kOp;
-                mbar_wait(&bars[B_OP_FULL + (u & 1)], (u >> 1) & 1);
-                mbar_wait(&bars[B_OP_FULL + ((u + 1) & 1)], ((u + 1) >> 1) & 1);
+            // operand sources: fp32 -> converted planes in the two operand buffers (item u -> buffer u & 1);
+            //                  bf16 -> the TMA tiles themselves (item u -> load slot u % kNLd), read with SWIZZLE_128B descriptors
+            const uint32_t ld_base = smem_u32(smem + S::off_ld);
+            auto wait_item = [&](uint32_t g) {
+                if constexpr (BF) mbar_wait(&bars[B_LD_FULL + g % kNLd], (g / kNLd) & 1);
+                else mbar_wait(&bars[B_OP_FULL + (g & 1)], (g >> 1) & 1);
+            };
+            auto free_item = [&](uint32_t g) {
+                if constexpr (BF) commit_to(&bars[B_LD_EMPTY + g % kNLd]);
+                else commit_to(&bars[B_OP_EMPTY + (g & 1)]);
+            };
+            auto item_addr = [&](uint32_t g) { return BF ? ld_base + (g % kNLd) * T::kSlot : op_base + (g & 1) * T::kOp; };
+            auto issue_s = [&](int k) {            // S(k) = Q K^T from items u (Q) and u+1 (K)
+                const uint32_t qb = item_addr(u), kb = item_addr(u + 1);
+                wait_item(u); wait_item(u + 1);
                 mbar_wait(&bars[B_S_EMPTY], (k & 1) ^ 1);
                 tc_fence_after();
                 CCA_STAMP(2);
                 for (int ks = 0; ks < KQ; ++ks) {
-                    const uint32_t ao = ks * 2 * T::kPlane;
-                    mma_split3<TERMS>(tmem, smem_desc(qb + ao, T::kPlane, 128), smem_desc(qb + 8 * T::kPlane + ao, T::kPlane, 128),
+                    if constexpr (BF) {
+                        mma_split3<1>(tmem, smem_desc(qb + ks * 32, 16, 1024, kSw128), 0, smem_desc(kb + ks * 32, 16, 1024, kSw128), 0,
+                                      idesc_s, ks > 0);
+                    } else {
+                        const uint32_t ao = ks * 2 * T::kPlane;
+                        mma_split3<3>(tmem, smem_desc(qb + ao, T::kPlane, 128), smem_desc(qb + 8 * T::kPlane + ao, T::kPlane, 128),
                                       smem_desc(kb + ao, T::kPlane, 128), smem_desc(kb + 8 * T::kPlane + ao, T::kPlane, 128),
                                       idesc_s, ks > 0);
+                    }
                 }
                 commit_to(&bars[B_S_FULL]);
-                commit_to(&bars[B_OP_EMPTY + (u & 1)]);
-                commit_to(&bars[B_OP_EMPTY + ((u + 1) & 1)]);
+                free_item(u); free_item(u + 1);
                 u += 2;
             };
             issue_s(0);
@@ -225,9 +243,9 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                 const uint32_t pbuf = tmem + kTmemP + (k & 1) * 128;
                 for (int n = 0; n < NCH; ++n, ++u, ++oc) {
                     if (n == qkpos && k + 1 < nk) issue_s(k + 1);
-                    const uint32_t vb = op_base + (u & 1) * T::kOp;
+                    const uint32_t vb = item_addr(u);
                     const uint32_t ob = oc % kNOB;
-                    mbar_wait(&bars[B_OP_FULL + (u & 1)], (u >> 1) & 1);
+                    wait_item(u);
                     mbar_wait(&bars[B_O_EMPTY + ob], ((oc / kNOB) & 1) ^ 1);
                     tc_fence_after();
                     CCA_STAMP(2);
@@ -236,10 +254,12 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
 #pragma unroll
                         for (int ks = 0; ks < LK / 16; ++ks) {
                             const uint32_t ph = pbuf + ks * 8, pl = ph + LK / 2;
-                            const uint64_t vh = smem_desc(vb + ks * 256, 128, T::kPlane);
-                            const uint64_t vl = smem_desc(vb + 8 * T::kPlane + ks * 256, 128, T::kPlane);
-                            mma_f16_ts(d, ph, vh, idesc_o, ks > 0);
-                            if constexpr (TERMS == 3) {
+                            if constexpr (BF) {
+                                mma_f16_ts(d, ph, smem_desc(vb + ks * 2048, 16, 1024, kSw128), idesc_o, ks > 0);
+                            } else {
+                                const uint64_t vh = smem_desc(vb + ks * 256, 128, T::kPlane);
+                                const uint64_t vl = smem_desc(vb + 8 * T::kPlane + ks * 256, 128, T::kPlane);
+                                mma_f16_ts(d, ph, vh, idesc_o, ks > 0);
                                 mma_f16_ts(d, ph, vl, idesc_o, true);
                                 mma_f16_ts(d, pl, vh, idesc_o, true);
                             }
@@ -247,7 +267,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                     }
                     __syncwarp();
                     commit_to(&bars[B_O_FULL + ob]);
-                    commit_to(&bars[B_OP_EMPTY + (u & 1)]);
+                    free_item(u);
                     CCA_STAMP(2);
                 }
                 commit_to(&bars[B_P_EMPTY + (k & 1)]);
@@ -316,7 +336,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
         // =============================== converters (256 threads) ===============================
         reg_dec<kRegsConv>();
         const int t = tid - kWarpConv0 * 32;
-        const uint32_t total = (uint32_t)nk * (2 + NCH);
+        const uint32_t total = BF ? 0u : (uint32_t)nk * (2 + NCH);     // bf16 tiles need no conversion
         int dbg_n = t == 0 ? 0 : 512;
         for (uint32_t g = 0; g < total; ++g) {
             const int slot = g % kNLd, ob = g & 1;

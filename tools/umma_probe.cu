@@ -112,6 +112,67 @@ __global__ void __launch_bounds__(128) umma_probe(const float *A, const float *B
     if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+// SWIZZLE_128B operands exactly as a bf16 TMA tile lands them: [rows][64 bf16 = 128 B], 16-byte chunk c of row r at c ^ (r & 7).
+//   D4 = A * B^T : A [128][64] and B [112][64] as K-major SW128 tiles (k-step = +32 B inside the swizzled row)
+//   D5 = P * V   : P no-swizzle K-major planes (A), V [112 rows = k][64 = mn] as an MN-major SW128 tile (k-step = +2048 B)
+__global__ void __launch_bounds__(128) umma_sw128_probe(const float *A, const float *B1, const float *P, const float *V,
+                                                        float *D4, float *D5)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t *sA = smem;                 // 128 rows x 128 B
+    uint8_t *sB = sA + 128 * 128;       // 112 rows x 128 B
+    uint8_t *sV = sB + 112 * 128;       // 112 rows x 128 B  (+ pad to keep 1024 alignment)
+    uint8_t *sP = sV + 112 * 128;       // 14 planes x 128 rows x 16 B
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc<256>(&tmem_base_s);
+    auto put_sw = [](uint8_t *tile, int row, int chunk, const float *src) {
+        __nv_bfloat16 v[8];
+        for (int i = 0; i < 8; ++i) v[i] = __float2bfloat16_rn(src[i]);
+        *reinterpret_cast<uint4 *>(tile + row * 128 + ((chunk ^ (row & 7)) * 16)) = *reinterpret_cast<uint4 *>(v);
+    };
+    for (int t = tid; t < 128 * 8; t += 128) put_sw(sA, t / 8, t % 8, A + (t / 8) * 64 + (t % 8) * 8);
+    for (int t = tid; t < 112 * 8; t += 128) put_sw(sB, t / 8, t % 8, B1 + (t / 8) * 64 + (t % 8) * 8);
+    for (int t = tid; t < 112 * 8; t += 128) put_sw(sV, t / 8, t % 8, V + (t / 8) * 64 + (t % 8) * 8);
+    for (int t = tid; t < 128 * 14; t += 128) {
+        const int r = t % 128, c = t / 128;
+        __nv_bfloat16 v[8];
+        for (int i = 0; i < 8; ++i) v[i] = __float2bfloat16_rn(P[r * 112 + c * 8 + i]);
+        *reinterpret_cast<uint4 *>(sP + plane_off(r, c, 128)) = *reinterpret_cast<uint4 *>(v);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    if (tid == 0) {
+        constexpr uint32_t id4 = instr_desc(kFmtBF16, kFmtBF16, 128, 112, false, false);
+        for (int ks = 0; ks < 4; ++ks)
+            mma_f16(tmem, smem_desc(smem_u32(sA) + ks * 32, 16, 1024, 2), smem_desc(smem_u32(sB) + ks * 32, 16, 1024, 2), id4, ks > 0);
+        constexpr uint32_t id5 = instr_desc(kFmtBF16, kFmtBF16, 128, 64, false, true);
+        for (int ks = 0; ks < 7; ++ks)
+            mma_f16(tmem + 128, smem_desc(smem_u32(sP) + ks * 2 * 128 * 16, 128 * 16, 128), smem_desc(smem_u32(sV) + ks * 2048, 16, 1024, 2), id5, ks > 0);
+        mma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    uint32_t r[16];
+    for (int c0 = 0; c0 < 112; c0 += 16) {
+        tmem_ld16(tmem + lane_base + c0, r); tmem_ld_wait();
+        for (int i = 0; i < 16; ++i) D4[tid * 112 + c0 + i] = __uint_as_float(r[i]);
+    }
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+        tmem_ld16(tmem + 128 + lane_base + c0, r); tmem_ld_wait();
+        for (int i = 0; i < 16; ++i) D5[tid * 64 + c0 + i] = __uint_as_float(r[i]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
 // TMA probe: load a row box and a column box of an NHWC fp32 tensor with SWIZZLE_128B, dump raw smem, store back.
 __global__ void __launch_bounds__(128) tma_probe(const __grid_constant__ CUtensorMap map_row, const __grid_constant__ CUtensorMap map_col,
                                                  const __grid_constant__ CUtensorMap map_out, float *dump_row, float *dump_col,
@@ -175,6 +236,21 @@ int main()
     for (int m = 0; m < 128; ++m) for (int n = 0; n < N2; ++n) {
         double s = 0; for (int k = 0; k < KP; ++k) s += (double)bf(P[m * KP + k]) * bf(V[k * N2 + n]);
         e2 = fmax(e2, fabs(s - D2[m * N2 + n]));
+    }
+    {
+        float *dD4, *dD5;
+        CK(cudaMalloc(&dD4, 128 * 112 * 4)); CK(cudaMalloc(&dD5, 128 * 64 * 4));
+        const size_t sm2 = 128 * 128 + 112 * 128 * 2 + 14 * 128 * 16 + 2048;
+        CK(cudaFuncSetAttribute(umma_sw128_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+        umma_sw128_probe<<<1, 128, sm2>>>(dA, dB1, dP, dV, dD4, dD5);
+        CK(cudaDeviceSynchronize());
+        std::vector<float> D4(128 * 112), D5(128 * 64);
+        CK(cudaMemcpy(D4.data(), dD4, D4.size() * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(D5.data(), dD5, D5.size() * 4, cudaMemcpyDeviceToHost));
+        double e4 = 0, e5 = 0;
+        for (size_t i = 0; i < D4.size(); ++i) e4 = fmax(e4, fabs((double)D4[i] - D1[i]));
+        for (size_t i = 0; i < D5.size(); ++i) e5 = fmax(e5, fabs((double)D5[i] - D2[i]));
+        printf("UMMA SW128 K-major x K-major (TMA-style bf16 tiles) vs no-swizzle result: max abs diff %.3e  %s\n", e4, e4 < 1e-3 ? "OK" : "MISMATCH");
+        printf("UMMA K-major planes x SW128 MN-major tile          vs no-swizzle result: max abs diff %.3e  %s\n", e5, e5 < 1e-3 ? "OK" : "MISMATCH");
     }
     double e3 = 0;
     for (size_t i = 0; i < D3.size(); ++i) e3 = fmax(e3, fabs((double)D3[i] - D2[i]));
