@@ -40,11 +40,14 @@ static_assert(reg_pool_ok(kRegsSoft, kRegsEpi), "setmaxnreg pool");
 constexpr int kNOut = 3;            // staging slots
 constexpr int kNLdMax = 6;          // load ring: 3 slots (fp32: 28 KB each) or 6 (bf16: 14 KB each, consumed by UMMA in place)
 
-enum { MODE_FUSED = 0, MODE_COL_ONLY = 2, MODE_ROW_ONLY = 3 };
+enum { MODE_FUSED = 0, MODE_DYNAMIC = 1, MODE_COL_ONLY = 2, MODE_ROW_ONLY = 3 };
 
 struct FwdParams {
     int B, H, W, C, Cq;
-    int mode;              // MODE_FUSED: col(b) row(b) interleaved per sample; *_ONLY: one pass per launch
+    int mode;              // MODE_DYNAMIC: one launch, lines claimed from two global queues (a row line only once its
+                           // sample's column lines are complete); MODE_FUSED: one launch, static interleaved order;
+                           // *_ONLY: one pass per launch
+    unsigned int *sched;   // [2] next column line / next row line to hand out (MODE_DYNAMIC)
     float2 *stats;         // [B,H,W] (m_c, l_c) of the column branch
     float *lse;            // [B,H,W]
     unsigned int *done;    // [B] column lines completed (MODE_FUSED only)
@@ -55,7 +58,7 @@ struct Item { int col, b, i, L; };
 
 __device__ __forceinline__ int total_items(const FwdParams &p)
 {
-    return p.mode == MODE_FUSED ? p.B * (p.W + p.H) : (p.mode == MODE_COL_ONLY ? p.B * p.W : p.B * p.H);
+    return p.mode <= MODE_DYNAMIC ? p.B * (p.W + p.H) : (p.mode == MODE_COL_ONLY ? p.B * p.W : p.B * p.H);
 }
 __device__ __forceinline__ Item decode_item(const FwdParams &p, int idx)
 {
@@ -96,12 +99,21 @@ template <int LK, bool BF> struct FwdSmem {
     static constexpr int off_tail = off_op + (BF ? 0 : 2 * T::kOp); // pad: an M=128 MMA reads (128 - LK) rows past the last plane
     static constexpr int off_scale = off_tail + (128 - LK) * 16;          // float2 (sa, sb) [2][128]: softmax group -> epilogue group
     static constexpr int off_bar = off_scale + 2 * 128 * 8;
-    static constexpr int kBytes = off_bar + 384;
+    static constexpr int kBytes = off_bar + 8 * 52 + 2 * 8 * 16 + 32;
     static_assert(kBytes <= 232448, "shared memory budget");
 };
 
 enum { B_LD_FULL = 0, B_LD_EMPTY = 6, B_OP_FULL = 12, B_OP_EMPTY = 14, B_S_FULL = 16, B_S_EMPTY = 17, B_P_FULL = 18,
-       B_P_EMPTY = 20, B_O_FULL = 22, B_O_EMPTY = 24, B_OUT_FULL = 26, B_SC_EMPTY = 29, B_SC_FULL = 31, B_STAGED = 33, B_COUNT = 36 };
+       B_P_EMPTY = 20, B_O_FULL = 22, B_O_EMPTY = 24, B_OUT_FULL = 26, B_SC_EMPTY = 29, B_SC_FULL = 31, B_STAGED = 33, B_EARLY = 36,
+       B_FINAL = 44, B_COUNT = 52 };
+
+// Work distribution inside a CTA: the producer thread is the scheduler.  For the item that follows item j-1 it publishes
+//   EARLY[j] when it reaches the slot where the next item's Q/K would be slipped into the ring (kind: 1 = item, 2 = no more
+//            work, 0 = not decided yet -- e.g. only row lines are left and their sample's columns are not complete), and
+//   FINAL[j] the definitive answer (same as EARLY unless that was 0; then after the current item's last chunk).
+// Every role reads these records instead of computing a static schedule.
+struct Rec { int kind, col, b, i; };
+constexpr int kRecRing = 8;      // the producer never runs more than ~3 items ahead of the slowest role
 
 __device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p)
 {
@@ -132,13 +144,14 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
     constexpr int kNLd = S::kNLd;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S::off_bar);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::off_bar + 8 * B_COUNT);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::off_bar + 8 * B_COUNT + 2 * kRecRing * 16);
     float2 *scale = reinterpret_cast<float2 *>(smem + S::off_scale);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NCH = p.C / kNC;
     const int KQ = p.Cq / 16;                 // k-steps of the S MMA
     const int n_items = total_items(p);
-    const int nk = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items of this CTA
+    Rec *rec_early = reinterpret_cast<Rec *>(smem + S::off_bar + 8 * B_COUNT);
+    Rec *rec_final = rec_early + kRecRing;
     // ring order:  Q0 K0 | V0[0..qkpos) Q1 K1 V0[qkpos..NCH) | V1[0..qkpos) Q2 K2 ...   (Q,K of the next item are slipped in
     // after the first chunks of the current one, so neither S(k+1) nor the first P V chunk of an item waits for the other)
     const int qkpos = NCH >= 3 ? 2 : NCH - 1;
@@ -149,6 +162,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
         for (int i = 0; i < kNOB; ++i) { mbar_init(&bars[B_O_FULL + i], 1); mbar_init(&bars[B_O_EMPTY + i], 128); }
         for (int i = 0; i < kNOut; ++i) { mbar_init(&bars[B_OUT_FULL + i], 1); mbar_init(&bars[B_STAGED + i], 128); }
         for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_SC_EMPTY + i], 128); mbar_init(&bars[B_SC_FULL + i], 128); }
+        for (int i = 0; i < kRecRing; ++i) { mbar_init(&bars[B_EARLY + i], 1); mbar_init(&bars[B_FINAL + i], 1); }
         mbar_init(&bars[B_S_FULL], 1); mbar_init(&bars[B_S_EMPTY], 128);
         for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_P_FULL + i], 128); mbar_init(&bars[B_P_EMPTY + i], 1); }
         fence_mbar_init();
@@ -161,7 +175,26 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    auto item_of = [&](int k) { return decode_item(p, (int)blockIdx.x + k * (int)gridDim.x); };
+    // ---- item records (see Rec): blocking / non-blocking readers used by every role
+    auto rec_item = [&](const Rec &r) { Item it; it.col = r.col; it.b = r.b; it.i = r.i; it.L = r.col ? p.H : p.W; return it; };
+    auto early_kind = [&](int j, Item &it) {                 // blocking on the early decision only
+        mbar_wait(&bars[B_EARLY + (j & (kRecRing - 1))], (j / kRecRing) & 1);
+        const Rec r = rec_early[j & (kRecRing - 1)];
+        if (r.kind == 1) it = rec_item(r);
+        return r.kind;
+    };
+    auto get_item = [&](int j, Item &it) {                   // blocking on the definitive answer; false = no more work
+        mbar_wait(&bars[B_FINAL + (j & (kRecRing - 1))], (j / kRecRing) & 1);
+        const Rec r = rec_final[j & (kRecRing - 1)];
+        if (r.kind == 1) it = rec_item(r);
+        return r.kind == 1;
+    };
+    auto try_item = [&](int j, Item &it) {                   // non-blocking: 1 item, 2 end, -1 not known yet
+        if (!mbar_try_wait(&bars[B_FINAL + (j & (kRecRing - 1))], (j / kRecRing) & 1)) return -1;
+        const Rec r = rec_final[j & (kRecRing - 1)];
+        if (r.kind == 1) it = rec_item(r);
+        return r.kind;
+    };
 
     if (warp >= kWarpProducer) {
         reg_dec<kRegsMisc>();
@@ -182,15 +215,79 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                     if constexpr (!BF) tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, it.b);
                     ++g;
                 };
-                Item cur = item_of(0);
-                emit(&mqc, &mqr, 0, cur);
-                emit(&mkc, &mkr, 0, cur);
-                for (int k = 0; k < nk; ++k) {
+                // ---- scheduler: hand out the next line of this CTA
+                int static_k = 0;
+                auto try_fetch = [&](Item &it) -> int {            // 1 item, 2 no more work, 0 nothing available right now
+                    if (p.mode != MODE_DYNAMIC) {
+                        const int idx = (int)blockIdx.x + static_k * (int)gridDim.x;
+                        if (idx >= n_items) return 2;
+                        it = decode_item(p, idx);
+                        ++static_k;
+                        return 1;
+                    }
+                    const unsigned total_rows = (unsigned)(p.B * p.H), total_cols = (unsigned)(p.B * p.W);
+                    for (int attempt = 0; attempt < 4; ++attempt) {
+                        const unsigned r = ld_acquire(p.sched + 1);
+                        if (r < total_rows) {                      // rows are handed out in order, only when their sample is ready
+                            const unsigned b = r / (unsigned)p.H;
+                            if (ld_acquire(p.done + b) >= (unsigned)p.W) {
+                                if (atomicCAS(p.sched + 1, r, r + 1) == r) {
+                                    it.col = 0; it.b = (int)b; it.i = (int)(r - b * p.H); it.L = p.W;
+                                    return 1;
+                                }
+                                continue;                          // lost the race for this row line: look again
+                            }
+                        }
+                        if (ld_acquire(p.sched + 0) < total_cols) {
+                            const unsigned c = atomicAdd(p.sched + 0, 1u);
+                            if (c < total_cols) {
+                                it.col = 1; it.b = (int)(c / (unsigned)p.W); it.i = (int)(c - it.b * p.W); it.L = p.H;
+                                return 1;
+                            }
+                        }
+                        if (r >= total_rows) return 2;
+                        return 0;                                  // only row lines are left and they are not ready yet
+                    }
+                    return 0;
+                };
+                auto fetch_blocking = [&](Item &it) -> int {
+                    unsigned spins = 0;
+                    for (;;) {
+                        const int kd = try_fetch(it);
+                        if (kd) return kd;
+                        __nanosleep(256);
+                        if (++spins > (1u << 22)) __trap();
+                    }
+                };
+                auto publish = [&](int base, Rec *arr, int j, int kind, const Item &it) {
+                    Rec r; r.kind = kind; r.col = it.col; r.b = it.b; r.i = it.i;
+                    arr[j & (kRecRing - 1)] = r;
+                    mbar_arrive(&bars[base + (j & (kRecRing - 1))]);       // release: the record is visible to the waiters
+                };
+                Item cur;
+                cur.col = cur.b = cur.i = cur.L = 0;
+                int kind = fetch_blocking(cur);
+                publish(B_EARLY, rec_early, 0, kind, cur);
+                publish(B_FINAL, rec_final, 0, kind, cur);
+                if (kind == 1) { emit(&mqc, &mqr, 0, cur); emit(&mkc, &mkr, 0, cur); }
+                for (int k = 0; kind == 1; ++k) {
                     Item nxt = cur;
+                    int nkind = -1;                                 // -1: not decided yet
                     for (int n = 0; n < NCH; ++n) {
-                        if (n == qkpos && k + 1 < nk) { nxt = item_of(k + 1); emit(&mqc, &mqr, 0, nxt); emit(&mkc, &mkr, 0, nxt); }
+                        if (n == qkpos) {
+                            nkind = try_fetch(nxt);
+                            publish(B_EARLY, rec_early, k + 1, nkind, nxt);
+                            if (nkind != 0) publish(B_FINAL, rec_final, k + 1, nkind, nxt);
+                            if (nkind == 1) { emit(&mqc, &mqr, 0, nxt); emit(&mkc, &mkr, 0, nxt); }
+                        }
                         emit(&mvc, &mvr, n * kNC, cur);
                     }
+                    if (nkind == 0) {                               // decided late: after the last chunk of the current item
+                        nkind = fetch_blocking(nxt);
+                        publish(B_FINAL, rec_final, k + 1, nkind, nxt);
+                        if (nkind == 1) { emit(&mqc, &mqr, 0, nxt); emit(&mkc, &mkr, 0, nxt); }
+                    }
+                    kind = nkind;
                     cur = nxt;
                 }
             }
@@ -234,15 +331,21 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                 free_item(u); free_item(u + 1);
                 u += 2;
             };
-            issue_s(0);
-            for (int k = 0; k < nk; ++k) {
+            Item it_unused;
+            bool have = get_item(0, it_unused);
+            if (have) issue_s(0);
+            for (int k = 0; have; ++k) {
+                int nkind = -1;
                 CCA_STAMP(2);
                 mbar_wait(&bars[B_P_FULL + (k & 1)], (k >> 1) & 1);
                 tc_fence_after();
                 CCA_STAMP(2);
                 const uint32_t pbuf = tmem + kTmemP + (k & 1) * 128;
                 for (int n = 0; n < NCH; ++n, ++u, ++oc) {
-                    if (n == qkpos && k + 1 < nk) issue_s(k + 1);
+                    if (n == qkpos) {                              // same decision the producer took when it filled the ring
+                        nkind = early_kind(k + 1, it_unused);
+                        if (nkind == 1) issue_s(k + 1);
+                    }
                     const uint32_t vb = item_addr(u);
                     const uint32_t ob = oc % kNOB;
                     wait_item(u);
@@ -271,6 +374,10 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                     CCA_STAMP(2);
                 }
                 commit_to(&bars[B_P_EMPTY + (k & 1)]);
+                if (nkind == 0) {                                  // late decision: Q,K of the next item follow the last chunk
+                    have = get_item(k + 1, it_unused);
+                    if (have) issue_s(k + 1);
+                } else have = nkind == 1;
             }
         } else if (warp == kWarpStore) {
             // =============================== store warp (one lane): staging slots <-> global ===============================
@@ -278,55 +385,66 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             // partial prefetched by TMA, two chunks ahead), and once the group has staged the merged tile, TMA-store it.
             // Column items are published (per-sample counter) after their last store has completed.
             if (lane == 0) {
-                const uint32_t total_chunks = (uint32_t)nk * NCH;
-                uint32_t prep = 0;                         // chunks prepared so far
+                uint32_t prep = 0;                         // chunks prepared so far (chunk c belongs to item c / NCH)
                 int pub_k = 0;                             // items [0, pub_k) are published / need no publishing
-                auto chunk_item = [&](uint32_t c) { return (int)(c / NCH); };
-                auto can_prepare = [&](uint32_t c) {       // a row chunk must not wait for a column item this warp has yet to publish
-                    const Item nx = item_of(chunk_item(c));
+                // a row chunk must not wait for a column item this warp has yet to publish (static fused order only:
+                // the dynamic scheduler hands out a row line only after all column lines of its sample were published)
+                auto can_prepare = [&](uint32_t c) {
+                    Item nx;
+                    if (try_item((int)(c / NCH), nx) != 1) return false;
                     if (nx.col || p.mode != MODE_FUSED) return true;
-                    for (int j = pub_k; j < chunk_item(c); ++j) {
-                        const Item pj = item_of(j);
-                        if (pj.col && pj.b == nx.b) return false;
+                    for (int j = pub_k; j < (int)(c / NCH); ++j) {
+                        Item pj;
+                        if (try_item(j, pj) == 1 && pj.col && pj.b == nx.b) return false;
                     }
                     return true;
                 };
-                auto prepare = [&](uint32_t c) {
-                    const Item it = item_of(chunk_item(c));
+                auto prepare = [&](uint32_t c, const Item &it) {
                     const int n = c % NCH, os = c % kNOut;
                     if (it.col) { mbar_arrive(&bars[B_OUT_FULL + os]); return; }
-                    if (p.mode == MODE_FUSED) { wait_done(p.done + it.b, (unsigned)p.W); fence_proxy_async_all(); }
+                    if (p.mode <= MODE_DYNAMIC) { wait_done(p.done + it.b, (unsigned)p.W); fence_proxy_async_all(); }
                     uint8_t *dst = smem + S::off_out + os * T::kSlot;
                     mbar_expect_tx(&bars[B_OUT_FULL + os], T::kSlot);
                     tma_load_4d(dst, &mor, &bars[B_OUT_FULL + os], n * kNC, 0, it.i, it.b);
                     if constexpr (!BF) tma_load_4d(dst + T::kTile, &mor, &bars[B_OUT_FULL + os], n * kNC + 32, 0, it.i, it.b);
                 };
-                while (prep < total_chunks && prep < 2 && can_prepare(prep)) { prepare(prep); ++prep; }
-                for (uint32_t c = 0; c < total_chunks; ++c) {
-                    const int k = chunk_item(c), n = c % NCH, os = c % kNOut;
-                    const Item it = item_of(k);
-                    mbar_wait(&bars[B_STAGED + os], (c / kNOut) & 1);
-                    const uint8_t *slot = smem + S::off_out + os * T::kSlot;
+                Item it;
+                for (int k = 0; get_item(k, it); ++k) {
                     const CUtensorMap *mo = it.col ? &moc : &mor;
                     const int cw = it.col ? it.i : 0, ch = it.col ? 0 : it.i;
-                    tma_store_4d(mo, slot, n * kNC, cw, ch, it.b);
-                    if constexpr (!BF) tma_store_4d(mo, slot + T::kTile, n * kNC + 32, cw, ch, it.b);
-                    tma_store_commit();
-                    if (n == NCH - 1) {
-                        if (it.col && p.mode == MODE_FUSED) {
-                            // publish this column line: its stores (async proxy) and the stats written by the softmax group
-                            tma_store_wait_all<0>();
-                            fence_proxy_async_all();
-                            __threadfence();
-                            atomicAdd(p.done + it.b, 1u);
+                    for (int n = 0; n < NCH; ++n) {
+                        const uint32_t c = (uint32_t)k * NCH + n;
+                        const int os = c % kNOut;
+                        while (prep <= c) {                        // not prefetched: prepare the current chunk now
+                            tma_store_wait_read<1>();
+                            Item pi = it;
+                            if ((int)(prep / NCH) != k) get_item((int)(prep / NCH), pi);
+                            prepare(prep, pi);
+                            ++prep;
                         }
-                        pub_k = k + 1;
-                    }
-                    // keep two chunks prepared ahead; slot of chunk c+2 was last used by chunk c-1, whose store must have drained
-                    while (prep < total_chunks && prep <= c + 2 && can_prepare(prep)) {
-                        tma_store_wait_read<1>();
-                        prepare(prep);
-                        ++prep;
+                        mbar_wait(&bars[B_STAGED + os], (c / kNOut) & 1);
+                        const uint8_t *slot = smem + S::off_out + os * T::kSlot;
+                        tma_store_4d(mo, slot, n * kNC, cw, ch, it.b);
+                        if constexpr (!BF) tma_store_4d(mo, slot + T::kTile, n * kNC + 32, cw, ch, it.b);
+                        tma_store_commit();
+                        if (n == NCH - 1) {
+                            if (it.col && p.mode <= MODE_DYNAMIC) {
+                                // publish this column line: its stores (async proxy) and the stats written by the softmax group
+                                tma_store_wait_all<0>();
+                                fence_proxy_async_all();
+                                __threadfence();
+                                atomicAdd(p.done + it.b, 1u);
+                            }
+                            pub_k = k + 1;
+                        }
+                        // keep two chunks prepared ahead; slot of chunk c+2 was last used by chunk c-1, whose store must have drained
+                        while (prep <= c + 2 && can_prepare(prep)) {
+                            Item pi;
+                            try_item((int)(prep / NCH), pi);
+                            tma_store_wait_read<1>();
+                            prepare(prep, pi);
+                            ++prep;
+                        }
                     }
                 }
                 tma_store_wait_all<0>();
@@ -336,19 +454,40 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
         // =============================== converters (256 threads) ===============================
         reg_dec<kRegsConv>();
         const int t = tid - kWarpConv0 * 32;
-        const uint32_t total = BF ? 0u : (uint32_t)nk * (2 + NCH);     // bf16 tiles need no conversion
         int dbg_n = t == 0 ? 0 : 512;
-        for (uint32_t g = 0; g < total; ++g) {
-            const int slot = g % kNLd, ob = g & 1;
-            mbar_wait(&bars[B_LD_FULL + slot], (g / kNLd) & 1);
-            CCA_STAMP(1);
-            mbar_wait(&bars[B_OP_EMPTY + ob], ((g >> 1) & 1) ^ 1);
-            CCA_STAMP(1);
-            convert_slot<LK, BF>(smem + S::off_ld + slot * T::kSlot, smem + S::off_op + ob * T::kOp, t);
-            fence_proxy_async();
-            mbar_arrive(&bars[B_OP_FULL + ob]);
-            mbar_arrive(&bars[B_LD_EMPTY + slot]);
-            CCA_STAMP(1);
+        uint32_t g = 0;
+        auto convert_next = [&](int count) {                       // the next `count` ring slots, whatever they hold
+            for (int e = 0; e < count; ++e, ++g) {
+                const int slot = g % kNLd, ob = g & 1;
+                mbar_wait(&bars[B_LD_FULL + slot], (g / kNLd) & 1);
+                CCA_STAMP(1);
+                mbar_wait(&bars[B_OP_EMPTY + ob], ((g >> 1) & 1) ^ 1);
+                CCA_STAMP(1);
+                convert_slot<LK, BF>(smem + S::off_ld + slot * T::kSlot, smem + S::off_op + ob * T::kOp, t);
+                fence_proxy_async();
+                mbar_arrive(&bars[B_OP_FULL + ob]);
+                mbar_arrive(&bars[B_LD_EMPTY + slot]);
+                CCA_STAMP(1);
+            }
+        };
+        if constexpr (!BF) {                                       // bf16 tiles need no conversion
+            Item it;
+            bool have = get_item(0, it);
+            if (have) convert_next(2);                             // Q, K of the first item
+            for (int k = 0; have; ++k) {                           // mirrors the ring order chosen by the producer
+                int nkind = -1;
+                for (int n = 0; n < NCH; ++n) {
+                    if (n == qkpos) {
+                        nkind = early_kind(k + 1, it);
+                        if (nkind == 1) convert_next(2);
+                    }
+                    convert_next(1);
+                }
+                if (nkind == 0) {
+                    have = get_item(k + 1, it);
+                    if (have) convert_next(2);
+                } else have = nkind == 1;
+            }
         }
     } else if (warp >= 4) {
         // =============================== softmax group (128 threads, TMEM lane == query pixel) ===============================
@@ -356,8 +495,8 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
         const int r = tid - 128;
         const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         int dbg_n = r == 0 ? 0 : 512;
-        for (int k = 0; k < nk; ++k) {
-            const Item it = item_of(k);
+        Item it;
+        for (int k = 0; get_item(k, it); ++k) {
             const bool rvalid = r < it.L;
             CCA_STAMP(3);
             mbar_wait(&bars[B_S_FULL], k & 1);
@@ -381,7 +520,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
 #pragma unroll
             for (int j = 0; j < LK; ++j) { s[j] = exp2f(s[j] - msub); l += s[j]; }
             float sa = 0.f, sb = 0.f;
-            if (!it.col && p.mode == MODE_FUSED) wait_done(p.done + it.b, (unsigned)p.W);   // column stats of this sample complete
+            if (!it.col && p.mode <= MODE_DYNAMIC) wait_done(p.done + it.b, (unsigned)p.W);   // column stats of this sample complete
             if (rvalid) {
                 const long pix = it.col ? ((long)it.b * p.H + r) * p.W + it.i : ((long)it.b * p.H + it.i) * p.W + r;
                 const float mn = m * kLn2;                       // natural-log units
@@ -429,8 +568,8 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
         const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
         uint32_t oc = 0;
         int dbg_n = tid == 0 ? 0 : 512;
-        for (int k = 0; k < nk; ++k) {
-            const Item it = item_of(k);
+        Item it;
+        for (int k = 0; get_item(k, it); ++k) {
             float sa = 0.f, sb = 0.f;
             for (int n = 0; n < NCH; ++n, ++oc) {
                 const int os = oc % kNOut;
@@ -516,7 +655,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
 long long *g_dbg = nullptr;   // set through cca_b200__set_debug_buffer (profiling aid, not part of the ABI)
 
 template <int LK, bool BF>
-cudaError_t launch_fwd(const void *q, const void *k, const void *v, void *out, float *lse, float2 *stats, unsigned int *done,
+cudaError_t launch_fwd(const void *q, const void *k, const void *v, void *out, float *lse, float2 *stats, unsigned int *cnt,
                        Dims d, int mode, cudaStream_t st, const char **why)
 {
     CUtensorMap m[8];
@@ -530,35 +669,37 @@ cudaError_t launch_fwd(const void *q, const void *k, const void *v, void *out, f
             }
     FwdParams p;
     p.B = d.B; p.H = d.H; p.W = d.W; p.C = d.C; p.Cq = d.Cq;
-    p.mode = mode; p.stats = stats; p.lse = lse; p.done = done;
+    p.mode = mode; p.stats = stats; p.lse = lse; p.sched = cnt; p.done = cnt + 2;
     p.dbg = g_dbg ? g_dbg + (mode == MODE_ROW_ONLY ? 2560 : 0) : nullptr;
     auto kern = cca_tc_fwd_kernel<LK, BF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem<LK, BF>::kBytes);
     if (e != cudaSuccess) return e;
-    const int items = mode == MODE_FUSED ? d.B * (d.W + d.H) : (mode == MODE_COL_ONLY ? d.B * d.W : d.B * d.H);
+    const int items = mode <= MODE_DYNAMIC ? d.B * (d.W + d.H) : (mode == MODE_COL_ONLY ? d.B * d.W : d.B * d.H);
     const int grid = items < sm_count() ? items : sm_count();
     kern<<<grid, kThreads, FwdSmem<LK, BF>::kBytes, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], p);
     count_launch();
     return cudaGetLastError();
 }
 
-// Launch policy of the forward: 0 = two launches (column pass, row pass), 1 = one fused launch with per-sample
-// column->row scheduling.  Measured on B200 (B=8, C=512, 97x97): the fused launch moves 634 MB through DRAM instead of
-// 768 MB but loses more to dependency stalls (0.166 ms vs 0.156 ms), so two launches are the default for now.
+// Launch policy of the forward (CCA_B200_FUSED): 0 = two launches (column pass, row pass); 1 = ONE launch with dynamic
+// scheduling (lines are claimed from a column queue and a row queue; a row line only once the column lines of its sample
+// are complete, so the partial output and q,k,v are re-read from L2 and no CTA ever waits on another); 2 = one launch with
+// the static interleaved order (kept for comparison: it stalls on the column->row dependency).
 int g_fused = -1;
-bool use_fused()
+int fused_mode()
 {
     if (g_fused < 0) {
         const char *e = getenv("CCA_B200_FUSED");
-        g_fused = (e && e[0] == '1') ? 1 : 0;
+        g_fused = e ? atoi(e) : 0;
+        if (g_fused < 0 || g_fused > 2) g_fused = 0;
     }
-    return g_fused == 1;
+    return g_fused;
 }
 
 }  // namespace
 
 void set_tc_debug_buffer(void *p) { g_dbg = reinterpret_cast<long long *>(p); }
-void set_tc_two_pass(int on) { g_fused = on ? 0 : 1; }
+void set_tc_two_pass(int on) { g_fused = on == 1 ? 0 : (on == 0 ? 1 : 2); }   // 1: two launches, 0: dynamic fused, 2: static fused
 
 bool tc_forward_supported(Dims d, int dtype) { return tc::shape_supported(d, dtype); }
 
@@ -566,10 +707,10 @@ bool tc_forward_supported(Dims d, int dtype) { return tc::shape_supported(d, dty
 namespace {
 template <bool BF>
 cudaError_t launch_fwd_lk(int lk, const void *q, const void *k, const void *v, void *out, float *lse, float2 *stats,
-                          unsigned int *done, Dims d, int mode, cudaStream_t st, const char **why)
+                          unsigned int *cnt, Dims d, int mode, cudaStream_t st, const char **why)
 {
-    return lk == 80 ? launch_fwd<80, BF>(q, k, v, out, lse, stats, done, d, mode, st, why)
-                    : launch_fwd<112, BF>(q, k, v, out, lse, stats, done, d, mode, st, why);
+    return lk == 80 ? launch_fwd<80, BF>(q, k, v, out, lse, stats, cnt, d, mode, st, why)
+                    : launch_fwd<112, BF>(q, k, v, out, lse, stats, cnt, d, mode, st, why);
 }
 }  // namespace
 
@@ -577,17 +718,17 @@ cudaError_t tc_forward(const void *q, const void *k, const void *v, void *out, f
                        cudaStream_t st, const char **why)
 {
     float2 *stats = reinterpret_cast<float2 *>(ws);
-    unsigned int *done = reinterpret_cast<unsigned int *>(stats + (size_t)d.B * d.H * d.W);
+    unsigned int *cnt = reinterpret_cast<unsigned int *>(stats + (size_t)d.B * d.H * d.W);   // [2] queue heads, [B] columns done
     const int lkc = lk_for(d.H), lkr = lk_for(d.W);
     const bool bf = dtype == CCA_BF16;
     auto go = [&](int lk, int mode) {
-        return bf ? launch_fwd_lk<true>(lk, q, k, v, out, lse, stats, done, d, mode, st, why)
-                  : launch_fwd_lk<false>(lk, q, k, v, out, lse, stats, done, d, mode, st, why);
+        return bf ? launch_fwd_lk<true>(lk, q, k, v, out, lse, stats, cnt, d, mode, st, why)
+                  : launch_fwd_lk<false>(lk, q, k, v, out, lse, stats, cnt, d, mode, st, why);
     };
-    if (lkc == lkr && use_fused()) {
-        cudaError_t e = cudaMemsetAsync(done, 0, sizeof(unsigned int) * d.B, st);
+    if (lkc == lkr && fused_mode() != 0) {
+        cudaError_t e = cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * (d.B + 2), st);
         if (e != cudaSuccess) return e;
-        return go(lkc, MODE_FUSED);
+        return go(lkc, fused_mode() == 1 ? MODE_DYNAMIC : MODE_FUSED);
     }
     cudaError_t e = go(lkc, MODE_COL_ONLY);
     if (e != cudaSuccess) return e;

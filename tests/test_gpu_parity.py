@@ -158,12 +158,13 @@ def test_forward_fused_launch_matches_two_launch_mode():
         q, k, v = _rand_qkv(*shape, seed=31 + sum(shape))
         qd, kd, vd = q.to(dev), k.to(dev), v.to(dev)
         try:
-            hook(1)
+            hook(1)                                   # two launches
             ref_o, ref_l = cca_forward(qd, kd, vd, impl="tc")
-            hook(0)
-            for _ in range(4):
-                o, l = cca_forward(qd, kd, vd, impl="tc")
-                assert torch.equal(o, ref_o) and torch.equal(l, ref_l)
+            for mode in (0, 2):                       # one launch: dynamic scheduling / static interleaved order
+                hook(mode)
+                for _ in range(4):
+                    o, l = cca_forward(qd, kd, vd, impl="tc")
+                    assert torch.equal(o, ref_o) and torch.equal(l, ref_l)
         finally:
             hook(1)
 

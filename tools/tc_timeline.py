@@ -28,8 +28,9 @@ def timeit(tag):
     e1.record(); torch.cuda.synchronize()
     print(tag, "fwd ms", e0.elapsed_time(e1) / 20)
 tp = lib.cca_b200__set_two_pass; tp.argtypes = [ctypes.c_int]; tp.restype = None
-tp(0); timeit("fused launch  :")
-tp(1); timeit("two launches  :")
+tp(0); timeit("one launch, dynamic :")
+tp(2); timeit("one launch, static  :")
+tp(1); timeit("two launches        :")
 t = buf.cpu().view(2, 5, 512)
 names = ["producer(slot free->issue)", "converter(full, op_empty, done)", "mma", "softmax", "epilogue(top, out_full, o_full, tmem_ld done, sts done, staged)"]
 for ps, pname in enumerate(["FUSED / COLUMN pass", "ROW pass"]):
