@@ -82,7 +82,7 @@ size_t cca_b200_workspace_bytes(int which, int B, int Cq, int C, int H, int W, i
     const size_t pix = (size_t)B * H * W;
     // forward: per-pixel (m,l) of the column pass + per-sample completion counters of the fused launch;
     // backward: per-pixel delta = <dout, out> + the same counters
-    const size_t counters = (((size_t)(B + 2) * sizeof(unsigned int)) + 15) & ~(size_t)15;   // 2 queue heads + per-sample counters
+    const size_t counters = (((size_t)(2 * B + 2) * sizeof(unsigned int)) + 15) & ~(size_t)15;   // queue heads + per-sample counters
     return (which == CCA_WS_FORWARD ? pix * sizeof(float2) : pix * sizeof(float)) + counters;
 }
 

@@ -47,7 +47,8 @@ struct FwdParams {
     int mode;              // MODE_DYNAMIC: one launch, lines claimed from two global queues (a row line only once its
                            // sample's column lines are complete); MODE_FUSED: one launch, static interleaved order;
                            // *_ONLY: one pass per launch
-    unsigned int *sched;   // [2] next column line / next row line to hand out (MODE_DYNAMIC)
+    unsigned int *sched;   // [0] next column line to hand out, [1] first sample that may still have row lines (MODE_DYNAMIC)
+    unsigned int *rown;    // [B] next row line of each sample (MODE_DYNAMIC)
     float2 *stats;         // [B,H,W] (m_c, l_c) of the column branch
     float *lse;            // [B,H,W]
     unsigned int *done;    // [B] column lines completed (MODE_FUSED only)
@@ -225,30 +226,25 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                         ++static_k;
                         return 1;
                     }
-                    const unsigned total_rows = (unsigned)(p.B * p.H), total_cols = (unsigned)(p.B * p.W);
-                    for (int attempt = 0; attempt < 4; ++attempt) {
-                        const unsigned r = ld_acquire(p.sched + 1);
-                        if (r < total_rows) {                      // rows are handed out in order, only when their sample is ready
-                            const unsigned b = r / (unsigned)p.H;
-                            if (ld_acquire(p.done + b) >= (unsigned)p.W) {
-                                if (atomicCAS(p.sched + 1, r, r + 1) == r) {
-                                    it.col = 0; it.b = (int)b; it.i = (int)(r - b * p.H); it.L = p.W;
-                                    return 1;
-                                }
-                                continue;                          // lost the race for this row line: look again
-                            }
-                        }
-                        if (ld_acquire(p.sched + 0) < total_cols) {
-                            const unsigned c = atomicAdd(p.sched + 0, 1u);
-                            if (c < total_cols) {
-                                it.col = 1; it.b = (int)(c / (unsigned)p.W); it.i = (int)(c - it.b * p.W); it.L = p.H;
-                                return 1;
-                            }
-                        }
-                        if (r >= total_rows) return 2;
-                        return 0;                                  // only row lines are left and they are not ready yet
+                    // dynamic: row lines first (in sample order, only of samples whose column lines are all published),
+                    // else the next column line.  All claims are atomicAdd on per-queue counters: no CAS retry storms.
+                    const unsigned total_cols = (unsigned)(p.B * p.W);
+                    unsigned b = ld_acquire(p.sched + 1);             // first sample that may still have row lines to hand out
+                    bool rows_left = false;
+                    for (; b < (unsigned)p.B; ++b) {
+                        if (ld_acquire(p.done + b) < (unsigned)p.W) { rows_left = true; break; }   // not ready yet (keep sample order)
+                        const unsigned r = atomicAdd(p.rown + b, 1u);
+                        if (r < (unsigned)p.H) { it.col = 0; it.b = (int)b; it.i = (int)r; it.L = p.W; return 1; }
+                        atomicMax(p.sched + 1, b + 1);                // this sample's rows are all handed out
                     }
-                    return 0;
+                    if (ld_acquire(p.sched + 0) < total_cols) {
+                        const unsigned c = atomicAdd(p.sched + 0, 1u);
+                        if (c < total_cols) {
+                            it.col = 1; it.b = (int)(c / (unsigned)p.W); it.i = (int)(c - it.b * p.W); it.L = p.H;
+                            return 1;
+                        }
+                    }
+                    return rows_left ? 0 : 2;                          // 0: only row lines are left and they are not ready yet
                 };
                 auto fetch_blocking = [&](Item &it) -> int {
                     unsigned spins = 0;
@@ -669,7 +665,7 @@ cudaError_t launch_fwd(const void *q, const void *k, const void *v, void *out, f
             }
     FwdParams p;
     p.B = d.B; p.H = d.H; p.W = d.W; p.C = d.C; p.Cq = d.Cq;
-    p.mode = mode; p.stats = stats; p.lse = lse; p.sched = cnt; p.done = cnt + 2;
+    p.mode = mode; p.stats = stats; p.lse = lse; p.sched = cnt; p.done = cnt + 2; p.rown = cnt + 2 + d.B;
     p.dbg = g_dbg ? g_dbg + (mode == MODE_ROW_ONLY ? 2560 : 0) : nullptr;
     auto kern = cca_tc_fwd_kernel<LK, BF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem<LK, BF>::kBytes);
@@ -718,7 +714,7 @@ cudaError_t tc_forward(const void *q, const void *k, const void *v, void *out, f
                        cudaStream_t st, const char **why)
 {
     float2 *stats = reinterpret_cast<float2 *>(ws);
-    unsigned int *cnt = reinterpret_cast<unsigned int *>(stats + (size_t)d.B * d.H * d.W);   // [2] queue heads, [B] columns done
+    unsigned int *cnt = reinterpret_cast<unsigned int *>(stats + (size_t)d.B * d.H * d.W);   // [2] queue heads, [B] columns done, [B] rows handed out
     const int lkc = lk_for(d.H), lkr = lk_for(d.W);
     const bool bf = dtype == CCA_BF16;
     auto go = [&](int lk, int mode) {
@@ -726,7 +722,7 @@ cudaError_t tc_forward(const void *q, const void *k, const void *v, void *out, f
                   : launch_fwd_lk<false>(lk, q, k, v, out, lse, stats, cnt, d, mode, st, why);
     };
     if (lkc == lkr && fused_mode() != 0) {
-        cudaError_t e = cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * (d.B + 2), st);
+        cudaError_t e = cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * (2 * d.B + 2), st);
         if (e != cudaSuccess) return e;
         return go(lkc, fused_mode() == 1 ? MODE_DYNAMIC : MODE_FUSED);
     }

@@ -26,8 +26,8 @@ def test_library_exports_every_declared_symbol():
 def test_version_and_workspace_and_strerror_without_gpu():
     lib = capi.load()
     assert lib.cca_b200_version() == 100
-    assert lib.cca_b200_workspace_bytes(capi.CCA_WS_FORWARD, 8, 64, 512, 97, 97, capi.CCA_F32) == 8 * 97 * 97 * 8 + 48
-    assert lib.cca_b200_workspace_bytes(capi.CCA_WS_BACKWARD, 8, 64, 512, 97, 97, capi.CCA_F32) == 8 * 97 * 97 * 4 + 48
+    assert lib.cca_b200_workspace_bytes(capi.CCA_WS_FORWARD, 8, 64, 512, 97, 97, capi.CCA_F32) == 8 * 97 * 97 * 8 + 80
+    assert lib.cca_b200_workspace_bytes(capi.CCA_WS_BACKWARD, 8, 64, 512, 97, 97, capi.CCA_F32) == 8 * 97 * 97 * 4 + 80
     assert lib.cca_b200_strerror(0) == b"ok"
     assert b"unsupported" in lib.cca_b200_strerror(-2)
 
