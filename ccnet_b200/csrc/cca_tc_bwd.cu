@@ -301,22 +301,25 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
             mbar_wait(&bars[B_S_FULL + (k & 1)], (k >> 1) & 1);
             tc_fence_after();
             CCA_STAMP(3);
-            {
-                float s[LK];
-#pragma unroll
-                for (int c0 = 0; c0 < LK; c0 += 16) tmem_ld16(tsd + c0, reinterpret_cast<uint32_t *>(s + c0));
+            // both phases stream the TMEM row 16 columns at a time (small loops: the instruction footprint of a fully
+            // unrolled LK-element register array cost more than the extra tcgen05.wait::ld round trips)
+            mbar_wait(&bars[B_P_EMPTY], (k & 1) ^ 1);
+#pragma unroll 1
+            for (int c0 = 0; c0 < LK; c0 += 16) {
+                float s[16];
+                tmem_ld16(tsd + c0, reinterpret_cast<uint32_t *>(s));
                 tmem_ld_wait();
-                tc_fence_before();
 #pragma unroll
-                for (int j = 0; j < LK; ++j) {
+                for (int e = 0; e < 16; ++e) {
+                    const int j = c0 + e;
                     const bool ok = rvalid && j < p.L && !(p.col && j == r);
-                    s[j] = ok ? exp2f(s[j] * kLog2e - lse2) : 0.f;
+                    s[e] = ok ? exp2f(s[e] * kLog2e - lse2) : 0.f;
                 }
-                mbar_wait(&bars[B_P_EMPTY], (k & 1) ^ 1);
                 if (r < LK) {
 #pragma unroll
-                    for (int kc = 0; kc < T::kPP; ++kc) {
-                        const float *v8 = s + kc * 8;
+                    for (int h = 0; h < 2; ++h) {
+                        const int kc = c0 / 8 + h;
+                        const float *v8 = s + h * 8;
                         if constexpr (BF) {
                             *reinterpret_cast<uint4 *>(ph + kc * T::kPlane) =
                                 make_uint4(pack_bf16(v8[0], v8[1]), pack_bf16(v8[2], v8[3]), pack_bf16(v8[4], v8[5]), pack_bf16(v8[6], v8[7]));
@@ -328,24 +331,24 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                         }
                     }
                 }
-                fence_proxy_async();
-                mbar_arrive(&bars[B_P_FULL]);
-                CCA_STAMP(3);
             }
+            tc_fence_before();
+            fence_proxy_async();
+            mbar_arrive(&bars[B_P_FULL]);
+            CCA_STAMP(3);
             // ---------------- dS = P * (dP - delta)   (all MMAs that read P have completed: DP_FULL is committed after them)
             mbar_wait(&bars[B_DP_FULL], k & 1);
             tc_fence_after();
             CCA_STAMP(3);
-            {
-                float dp[LK];
-#pragma unroll
-                for (int c0 = 0; c0 < LK; c0 += 16) tmem_ld16(tsd + c0, reinterpret_cast<uint32_t *>(dp + c0));
+#pragma unroll 1
+            for (int c0 = 0; c0 < LK; c0 += 16) {
+                float dp[16];
+                tmem_ld16(tsd + c0, reinterpret_cast<uint32_t *>(dp));
                 tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(&bars[B_S_EMPTY + (k & 1)]);
                 if (r < LK) {
 #pragma unroll
-                    for (int kc = 0; kc < T::kPP; ++kc) {
+                    for (int h = 0; h < 2; ++h) {
+                        const int kc = c0 / 8 + h;
                         const uint4 hi = *reinterpret_cast<const uint4 *>(ph + kc * T::kPlane);
                         uint4 lo = make_uint4(0, 0, 0, 0);
                         if constexpr (!BF) lo = *reinterpret_cast<const uint4 *>(pl + kc * T::kPlane);
@@ -354,8 +357,8 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const float p0 = bf_lo(hw[e]) + bf_lo(lw[e]), p1 = bf_hi(hw[e]) + bf_hi(lw[e]);
-                            ds[2 * e] = p0 * (dp[kc * 8 + 2 * e] - dl);
-                            ds[2 * e + 1] = p1 * (dp[kc * 8 + 2 * e + 1] - dl);
+                            ds[2 * e] = p0 * (dp[h * 8 + 2 * e] - dl);
+                            ds[2 * e + 1] = p1 * (dp[h * 8 + 2 * e + 1] - dl);
                         }
                         if constexpr (BF) {
                             *reinterpret_cast<uint4 *>(ph + kc * T::kPlane) =
@@ -368,10 +371,12 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                         }
                     }
                 }
-                fence_proxy_async();
-                mbar_arrive(&bars[B_DS_FULL]);
-                CCA_STAMP(3);
             }
+            tc_fence_before();
+            mbar_arrive(&bars[B_S_EMPTY + (k & 1)]);
+            fence_proxy_async();
+            mbar_arrive(&bars[B_DS_FULL]);
+            CCA_STAMP(3);
         }
     } else {
         // =============================== epilogue group (128 threads, TMEM lane == output pixel) ===============================

@@ -28,9 +28,9 @@ constexpr int kRegsConv = 56, kRegsMisc = 72;   // per kernel: kRegsSoft + kRegs
 // setmaxnreg moves registers through a per-CTA pool that only holds what the CTA itself released: the increases must be
 // covered by the decreases relative to the launch allocation of 96 regs/thread (640 threads):
 //   released 256*(96-56) + 128*(96-72) = 13312  >=  claimed 128*(168-96) + 128*(128-96) = 13312
-constexpr bool reg_pool_ok(int soft, int epi)
+constexpr bool reg_pool_ok(int soft, int epi, int conv = kRegsConv)
 {
-    return 256 * (96 - kRegsConv) + 128 * (96 - kRegsMisc) >= 128 * (soft - 96) + 128 * (epi - 96);
+    return 256 * (96 - conv) + 128 * (96 - kRegsMisc) >= 128 * (soft - 96) + 128 * (epi - 96);
 }
 
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -114,6 +114,36 @@ __device__ __forceinline__ void convert_slot(const uint8_t *slot, uint8_t *op, i
         split8(v, hi, lo);
         *reinterpret_cast<uint4 *>(dh + j * T::kPlane) = hi;
         *reinterpret_cast<uint4 *>(dl + j * T::kPlane) = lo;
+    }
+}
+
+// fp32 tile -> bf16 hi/lo planes IN PLACE (the planes take exactly the bytes of the two fp32 tiles): every converter thread
+// reads and splits its 128 B first, all 256 meet on named barrier 1, then they overwrite the slot.
+template <int LK>
+__device__ __forceinline__ void convert_slot_inplace(uint8_t *slot, int t)
+{
+    using T = Tiles<LK, false>;
+    const int r = t & 127, half = t >> 7;
+    float4 raw[8];                                              // the thread's 32 channels; split only after the barrier (fewer live registers)
+    {
+        const int rr = r < LK ? r : LK - 1;                     // idle threads re-read the last row (unconditional loads keep raw[] in registers)
+        const uint8_t *src = slot + rr * 128 + half * T::kTile; // octets 0-3 live in tile 0, 4-7 in tile 1
+        const int sw = rr & 7;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) raw[j] = *reinterpret_cast<const float4 *>(src + ((j ^ sw) * 16));
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kConvThreads) : "memory");
+    if (r < LK) {
+        uint8_t *dh = slot + r * 16 + half * 4 * T::kPlane, *dl = dh + 8 * T::kPlane;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 a = raw[2 * j], b = raw[2 * j + 1];
+            const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            uint4 hi, lo;
+            split8(v, hi, lo);
+            *reinterpret_cast<uint4 *>(dh + j * T::kPlane) = hi;
+            *reinterpret_cast<uint4 *>(dl + j * T::kPlane) = lo;
+        }
     }
 }
 

@@ -35,10 +35,12 @@ using namespace tc;
 
 constexpr int kTmemCols = 512;      // S [0,128)   P double buffer (hi/lo) [128,256) [256,384)   O ring 2 x 64 [384,512)
 constexpr int kTmemP = 128, kTmemO = 384, kNOB = 2;
-constexpr int kRegsSoft = 168, kRegsEpi = 128;
-static_assert(reg_pool_ok(kRegsSoft, kRegsEpi), "setmaxnreg pool");
+// the in-place conversion keeps a whole 128 B row (split into hi/lo) live across a barrier: converters get 88 registers; the
+// softmax group streams its row from TMEM 16 columns at a time and needs few
+constexpr int kRegsSoft = 104, kRegsEpi = 128, kRegsConvF = 88;
+static_assert(reg_pool_ok(kRegsSoft, kRegsEpi, kRegsConvF), "setmaxnreg pool");
 constexpr int kNOut = 3;            // staging slots
-constexpr int kNLdMax = 6;          // load ring: 3 slots (fp32: 28 KB each) or 6 (bf16: 14 KB each, consumed by UMMA in place)
+constexpr int kNLdMax = 6;          // load ring: 5 slots (fp32: 28 KB each, converted to bf16 hi/lo planes IN PLACE) or 6 (bf16: 14 KB each)
 
 enum { MODE_FUSED = 0, MODE_DYNAMIC = 1, MODE_COL_ONLY = 2, MODE_ROW_ONLY = 3 };
 
@@ -93,20 +95,21 @@ __device__ __forceinline__ Item decode_item(const FwdParams &p, int idx)
 
 template <int LK, bool BF> struct FwdSmem {
     using T = Tiles<LK, BF>;
-    static constexpr int kNLd = BF ? 6 : 3;
-    static constexpr int off_ld = 0;                          // kNLd load slots
+    static constexpr int kNLd = BF ? 6 : 5;
+    static constexpr int off_ld = 0;                          // kNLd load slots; every slot is the UMMA operand itself: a bf16 tile as
+                                                              // loaded, an fp32 tile once the converters have rewritten it in place
     static constexpr int off_out = off_ld + kNLd * T::kSlot;  // kNOut out slots
-    static constexpr int off_op = off_out + kNOut * T::kSlot; // 2 operand buffers (fp32 only: bf16 tiles are UMMA operands as loaded)
-    static constexpr int off_tail = off_op + (BF ? 0 : 2 * T::kOp); // pad: an M=128 MMA reads (128 - LK) rows past the last plane
+    static constexpr int off_tail = off_out + kNOut * T::kSlot; // pad: an M=128 MMA reads (128 - LK) rows past the last plane of a slot
+                                                              // (the rows land in the next slot / the staging slots; they only feed S rows >= LK)
     static constexpr int off_scale = off_tail + (128 - LK) * 16;          // float2 (sa, sb) [2][128]: softmax group -> epilogue group
     static constexpr int off_bar = off_scale + 2 * 128 * 8;
-    static constexpr int kBytes = off_bar + 8 * 52 + 2 * 8 * 16 + 32;
+    static constexpr int kBytes = off_bar + 8 * 54 + 2 * 8 * 16 + 32;
     static_assert(kBytes <= 232448, "shared memory budget");
 };
 
-enum { B_LD_FULL = 0, B_LD_EMPTY = 6, B_OP_FULL = 12, B_OP_EMPTY = 14, B_S_FULL = 16, B_S_EMPTY = 17, B_P_FULL = 18,
-       B_P_EMPTY = 20, B_O_FULL = 22, B_O_EMPTY = 24, B_OUT_FULL = 26, B_SC_EMPTY = 29, B_SC_FULL = 31, B_STAGED = 33, B_EARLY = 36,
-       B_FINAL = 44, B_COUNT = 52 };
+enum { B_LD_FULL = 0, B_LD_EMPTY = 6, B_OP_FULL = 12, B_S_FULL = 18, B_S_EMPTY = 19, B_P_FULL = 20,
+       B_P_EMPTY = 22, B_O_FULL = 24, B_O_EMPTY = 26, B_OUT_FULL = 28, B_SC_EMPTY = 31, B_SC_FULL = 33, B_STAGED = 35, B_EARLY = 38,
+       B_FINAL = 46, B_COUNT = 54 };
 
 // Work distribution inside a CTA: the producer thread is the scheduler.  For the item that follows item j-1 it publishes
 //   EARLY[j] when it reaches the slot where the next item's Q/K would be slipped into the ring (kind: 1 = item, 2 = no more
@@ -158,8 +161,9 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
     const int qkpos = NCH >= 3 ? 2 : NCH - 1;
 
     if (tid == 0) {
-        for (int i = 0; i < kNLd; ++i) { mbar_init(&bars[B_LD_FULL + i], 1); mbar_init(&bars[B_LD_EMPTY + i], BF ? 1 : kConvThreads); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_OP_FULL + i], kConvThreads); mbar_init(&bars[B_OP_EMPTY + i], 1); }
+        for (int i = 0; i < kNLd; ++i) {
+            mbar_init(&bars[B_LD_FULL + i], 1); mbar_init(&bars[B_LD_EMPTY + i], 1); mbar_init(&bars[B_OP_FULL + i], kConvThreads);
+        }
         for (int i = 0; i < kNOB; ++i) { mbar_init(&bars[B_O_FULL + i], 1); mbar_init(&bars[B_O_EMPTY + i], 128); }
         for (int i = 0; i < kNOut; ++i) { mbar_init(&bars[B_OUT_FULL + i], 1); mbar_init(&bars[B_STAGED + i], 128); }
         for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_SC_EMPTY + i], 128); mbar_init(&bars[B_SC_FULL + i], 128); }
@@ -291,21 +295,18 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             // =============================== MMA issuer (whole warp, elect.sync inside) ===============================
             const uint32_t idesc_s = instr_desc(kFmtBF16, kFmtBF16, 128, LK, false, false);
             const uint32_t idesc_o = instr_desc(kFmtBF16, kFmtBF16, 128, kNC, false, true);
-            const uint32_t op_base = smem_u32(smem + S::off_op);
             uint32_t u = 0, oc = 0;
             int dbg_n = lane == 0 ? 0 : 512;
-            // operand sources: fp32 -> converted planes in the two operand buffers (item u -> buffer u & 1);
-            //                  bf16 -> the TMA tiles themselves (item u -> load slot u % kNLd), read with SWIZZLE_128B descriptors
+            // operand of ring item u = load slot u % kNLd: fp32 -> bf16 hi/lo planes written in place by the converters;
+            //                                              bf16 -> the TMA tile itself, read with SWIZZLE_128B descriptors
             const uint32_t ld_base = smem_u32(smem + S::off_ld);
             auto wait_item = [&](uint32_t g) {
-                if constexpr (BF) mbar_wait(&bars[B_LD_FULL + g % kNLd], (g / kNLd) & 1);
-                else mbar_wait(&bars[B_OP_FULL + (g & 1)], (g >> 1) & 1);
+                mbar_wait(&bars[(BF ? B_LD_FULL : B_OP_FULL) + g % kNLd], (g / kNLd) & 1);
             };
             auto free_item = [&](uint32_t g) {
-                if constexpr (BF) commit_to(&bars[B_LD_EMPTY + g % kNLd]);
-                else commit_to(&bars[B_OP_EMPTY + (g & 1)]);
+                commit_to(&bars[B_LD_EMPTY + g % kNLd]);
             };
-            auto item_addr = [&](uint32_t g) { return BF ? ld_base + (g % kNLd) * T::kSlot : op_base + (g & 1) * T::kOp; };
+            auto item_addr = [&](uint32_t g) { return ld_base + (g % kNLd) * T::kSlot; };
             auto issue_s = [&](int k) {            // S(k) = Q K^T from items u (Q) and u+1 (K)
                 const uint32_t qb = item_addr(u), kb = item_addr(u + 1);
                 wait_item(u); wait_item(u + 1);
@@ -448,21 +449,18 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
         }
     } else if (warp >= kWarpConv0) {
         // =============================== converters (256 threads) ===============================
-        reg_dec<kRegsConv>();
+        reg_dec<kRegsConvF>();
         const int t = tid - kWarpConv0 * 32;
         int dbg_n = t == 0 ? 0 : 512;
         uint32_t g = 0;
         auto convert_next = [&](int count) {                       // the next `count` ring slots, whatever they hold
             for (int e = 0; e < count; ++e, ++g) {
-                const int slot = g % kNLd, ob = g & 1;
+                const int slot = g % kNLd;
                 mbar_wait(&bars[B_LD_FULL + slot], (g / kNLd) & 1);
                 CCA_STAMP(1);
-                mbar_wait(&bars[B_OP_EMPTY + ob], ((g >> 1) & 1) ^ 1);
-                CCA_STAMP(1);
-                convert_slot<LK, BF>(smem + S::off_ld + slot * T::kSlot, smem + S::off_op + ob * T::kOp, t);
+                convert_slot_inplace<LK>(smem + S::off_ld + slot * T::kSlot, t);
                 fence_proxy_async();
-                mbar_arrive(&bars[B_OP_FULL + ob]);
-                mbar_arrive(&bars[B_LD_EMPTY + slot]);
+                mbar_arrive(&bars[B_OP_FULL + slot]);
                 CCA_STAMP(1);
             }
         };
@@ -498,23 +496,55 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             mbar_wait(&bars[B_S_FULL], k & 1);
             tc_fence_after();
             CCA_STAMP(3);
-            float s[LK];
-#pragma unroll
-            for (int c0 = 0; c0 < LK; c0 += 16) tmem_ld16(tl + c0, reinterpret_cast<uint32_t *>(s + c0));
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(&bars[B_S_EMPTY]);
+            // two streaming passes over the S row in TMEM, 16 columns at a time (small loops instead of a 112-element
+            // register array: the instruction footprint matters -- the unrolled version cost ~16K cycles on its first run)
+            // ---- pass 1: row max of the valid, unmasked logits (log2 units)
             float m = -INFINITY;
+#pragma unroll 1
+            for (int c0 = 0; c0 < LK; c0 += 16) {
+                float s[16];
+                tmem_ld16(tl + c0, reinterpret_cast<uint32_t *>(s));
+                tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < LK; ++j) {
-                const bool ok = j < it.L && !(it.col && j == r);
-                s[j] = ok ? s[j] * kLog2e : -INFINITY;
-                m = fmaxf(m, s[j]);
+                for (int e = 0; e < 16; ++e) {
+                    const int j = c0 + e;
+                    const bool ok = j < it.L && !(it.col && j == r);
+                    m = fmaxf(m, ok ? s[e] * kLog2e : -INFINITY);
+                }
             }
             const float msub = (m == -INFINITY) ? 0.f : m;      // fully masked row (L == 1 in a column item)
+            // ---- pass 2: P = exp2(s - m) -> TMEM as packed bf16 pairs (hi at [pdst, +LK/2), lo at [pdst+LK/2, +LK/2)), row sum
+            CCA_STAMP(3);
+            mbar_wait(&bars[B_P_EMPTY + (k & 1)], ((k >> 1) & 1) ^ 1);    // P V of item k-2 has finished reading this buffer
+            tc_fence_after();
+            const uint32_t pdst = tl + kTmemP + (k & 1) * 128;
             float l = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < LK; c0 += 16) {
+                float s[16];
+                tmem_ld16(tl + c0, reinterpret_cast<uint32_t *>(s));
+                tmem_ld_wait();
+                uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int j = 0; j < LK; ++j) { s[j] = exp2f(s[j] - msub); l += s[j]; }
+                for (int e = 0; e < 8; ++e) {
+                    const int j = c0 + 2 * e;
+                    const bool ok0 = rvalid && j < it.L && !(it.col && j == r);
+                    const bool ok1 = rvalid && j + 1 < it.L && !(it.col && j + 1 == r);
+                    const float p0 = ok0 ? exp2f(s[2 * e] * kLog2e - msub) : 0.f;
+                    const float p1 = ok1 ? exp2f(s[2 * e + 1] * kLog2e - msub) : 0.f;
+                    l += p0 + p1;
+                    if constexpr (BF) hi[e] = pack_bf16(p0, p1);
+                    else split2(p0, p1, hi[e], lo[e]);
+                }
+                tmem_st8(pdst + c0 / 2, hi);
+                if constexpr (!BF) tmem_st8(pdst + LK / 2 + c0 / 2, lo);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bars[B_P_FULL + (k & 1)]);
+            mbar_arrive(&bars[B_S_EMPTY]);
+            CCA_STAMP(3);
+            // ---- per-pixel statistics / merge scales (off the MMA's critical path now)
             float sa = 0.f, sb = 0.f;
             if (!it.col && p.mode <= MODE_DYNAMIC) wait_done(p.done + it.b, (unsigned)p.W);   // column stats of this sample complete
             if (rvalid) {
@@ -536,26 +566,6 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             mbar_wait(&bars[B_SC_EMPTY + (k & 1)], ((k >> 1) & 1) ^ 1);   // epilogue has consumed the scales of item k-2
             scale[(k & 1) * 128 + r] = make_float2(sa, sb);
             mbar_arrive(&bars[B_SC_FULL + (k & 1)]);          // release: scales and the stats / lse written above
-            // ---------------- P -> TMEM as packed bf16 pairs: hi at [kTmemP, +LK/2), lo at [kTmemP+LK/2, +LK/2)
-            CCA_STAMP(3);
-            mbar_wait(&bars[B_P_EMPTY + (k & 1)], ((k >> 1) & 1) ^ 1);    // P V of item k-2 has finished reading this buffer
-            tc_fence_after();
-            const uint32_t pdst = tl + kTmemP + (k & 1) * 128;
-#pragma unroll
-            for (int c0 = 0; c0 < LK / 2; c0 += 8) {
-                uint32_t hi[8], lo[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    if constexpr (BF) hi[e] = pack_bf16(s[2 * (c0 + e)], s[2 * (c0 + e) + 1]);
-                    else split2(s[2 * (c0 + e)], s[2 * (c0 + e) + 1], hi[e], lo[e]);
-                }
-                tmem_st8(pdst + c0, hi);
-                if constexpr (!BF) tmem_st8(pdst + LK / 2 + c0, lo);
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&bars[B_P_FULL + (k & 1)]);
-            CCA_STAMP(3);
         }
     } else {
         // =============================== epilogue group (128 threads, TMEM lane == query pixel) ===============================

@@ -246,7 +246,11 @@ def test_module_vs_golden_fwd_bwd(golden):
         1.0, float(np.abs(golden["dx"]).max()))
     for n, p in m.named_parameters():
         ref = torch.from_numpy(golden["d_" + n])
-        tol = 2e-3 * max(1.0, ref.abs().max().item())
+        # a conv's bias gradient is the plain sum of the same per-pixel gradients its weight gradient weighs by x, so both
+        # carry the same absolute rounding error; key_conv.bias in particular cancels to exactly 0 in exact arithmetic
+        # (softmax shift invariance), so its own magnitude (~1e-5) says nothing about the scale of the summands (~1e3).
+        scale = torch.from_numpy(golden["d_" + n.replace(".bias", ".weight")]).abs().max().item()
+        tol = 2e-3 * max(1.0, ref.abs().max().item()) if not n.endswith(".bias") else max(2e-3, 1e-5 * scale)
         assert (p.grad.cpu() - ref).abs().max().item() <= tol, n
 
 
