@@ -33,6 +33,20 @@ size_t esize(int dtype) { return dtype == CCA_F32 ? 4 : 2; }
 }  // namespace
 
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+static int g_l2_hints = -1;
+static double g_l2_keep_mb = 80.0;
+int tc_l2_hints()
+{
+    if (g_l2_hints < 0) {
+        const char *e = getenv("CCA_B200_L2HINT"), *k = getenv("CCA_B200_L2KEEP_MB");
+        g_l2_hints = e ? (atoi(e) != 0) : 0;      // off by default: no gain measured with two launches per pass
+        if (k && atof(k) >= 0.0) g_l2_keep_mb = atof(k);
+    }
+    return g_l2_hints;
+}
+double tc_l2_keep_mb() { tc_l2_hints(); return g_l2_keep_mb; }
+void set_tc_l2_hints(int on, double keep_mb) { g_l2_hints = on != 0; g_l2_keep_mb = keep_mb; }
 }  // namespace cca
 
 using namespace cca;
@@ -45,6 +59,8 @@ CCA_API void cca_b200__set_debug_buffer(void *p) { set_tc_debug_buffer(p); }
 // A/B aid: run the tensor-core forward as two launches (column pass, row pass) instead of the fused launch
 CCA_API void cca_b200__set_two_pass(int on) { set_tc_two_pass(on); }
 CCA_API void cca_b200__set_bwd_debug_buffer(void *p) { set_tc_bwd_debug_buffer(p); }
+// A/B aid: L2 eviction hints on / off and the evict_last budget in MB
+CCA_API void cca_b200__set_l2_hints(int on, double keep_mb) { set_tc_l2_hints(on, keep_mb); }
 const char *cca_b200_last_error(void) { return g_err; }
 const char *cca_b200_strerror(int s)
 {

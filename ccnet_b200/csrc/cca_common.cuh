@@ -51,5 +51,9 @@ void count_launch(int n = 1);
 void set_tc_debug_buffer(void *p);
 void set_tc_two_pass(int on);
 void set_tc_bwd_debug_buffer(void *p);
+// L2 eviction hints of the tensor-core kernels (CCA_B200_L2HINT = 0/1, CCA_B200_L2KEEP_MB = budget of evict_last data)
+int tc_l2_hints();
+double tc_l2_keep_mb();
+void set_tc_l2_hints(int on, double keep_mb);
 
 }  // namespace cca

@@ -25,12 +25,16 @@ using namespace tc;
 
 constexpr int kTmemCols = 512;      // S / dP double buffer: [0,128) [128,256)   O0: [256,320)   O1: [320,384)
 constexpr int kTmemO = 256;
-constexpr int kRegsSoft = 152, kRegsEpi = 144;
-static_assert(reg_pool_ok(kRegsSoft, kRegsEpi), "setmaxnreg pool");
+// converters keep a whole 128 B row live across the barrier of the in-place conversion (88 registers); the P/dS group streams
+// its rows from TMEM 16 columns at a time
+constexpr int kRegsSoft = 104, kRegsEpi = 128, kRegsConvB = 88;
+static_assert(reg_pool_ok(kRegsSoft, kRegsEpi, kRegsConvB), "setmaxnreg pool");
 
 struct BwdParams {
     int B, H, W, C, Cq;
     int L, NL, col;
+    int hints, keep_from;  // L2 eviction hints: the column pass keeps (evict_last) the lines of samples >= keep_from for the row
+                           // pass, which walks the samples backwards; everything else streams (evict_first)
     const float *lse;
     const float *delta;
     long long *dbg;
@@ -41,27 +45,25 @@ struct BwdParams {
         if (p.dbg && blockIdx.x == 0 && dbg_n < 512) p.dbg[(role) * 512 + dbg_n++] = clock64();  \
     } while (0)
 
-constexpr int kNOp = 3;             // rotating operand buffers
-
 template <int LK, bool BF> struct BwdSmem {
     using T = Tiles<LK, BF>;
-    static constexpr int kNLd = BF ? 6 : 2;                // bf16 tiles are consumed by UMMA in place: deeper ring, no operand buffers
+    static constexpr int kNLd = BF ? 6 : 5;                // every slot is the UMMA operand itself: a bf16 tile as loaded, an fp32
+                                                           // tile once the converters have rewritten it in place (hi/lo planes)
     static constexpr int off_ld = 0;                       // kNLd load slots
     static constexpr int off_out = off_ld + kNLd * T::kSlot; // 1 out slot (the epilogue has slack; the store warp drives it)
-    static constexpr int off_p = off_out + T::kSlot;       // P / dS planes (hi, lo); over-reads land in the operand buffers / pad
-    static constexpr int off_op = off_p + T::kP;           // kNOp operand buffers (fp32 only)
-    static constexpr int off_tail = off_op + (BF ? (16 - LK / 8) * T::kPlane : kNOp * T::kOp); // bf16: pad for the P^T over-read (16 planes)
+    static constexpr int off_p = off_out + T::kSlot;       // P / dS planes (hi, lo); M=128 over-reads of a slot land in the next slot / here
+    static constexpr int off_tail = off_p + T::kP + (16 - LK / 8) * T::kPlane;   // pad for the P^T over-read (16 planes of 8 key pixels)
     static constexpr int off_bar = off_tail + (128 - LK) * 16 + 256;
     static constexpr int kBytes = off_bar + 320;
     static_assert(kBytes <= 232448, "shared memory budget");
 };
 
-enum { B_LD_FULL = 0, B_LD_EMPTY = 6, B_OP_FULL = 12, B_OP_EMPTY = 15, B_S_FULL = 18, B_S_EMPTY = 20, B_P_FULL = 22,
+enum { B_LD_FULL = 0, B_LD_EMPTY = 6, B_OP_FULL = 12, B_S_FULL = 18, B_S_EMPTY = 20, B_P_FULL = 22,
        B_P_EMPTY = 23, B_O_FULL = 24, B_O_EMPTY = 26, B_OUT_FULL = 28, B_STAGED = 29, B_DP_FULL = 30, B_DS_FULL = 31,
        B_COUNT = 32 };
 
-// Per line the ring carries  Q K (V_n dO_n)* Q K ; item g is converted into operand buffer g % 3, so the conversion of
-// the next chunk overlaps the MMAs of the current one.  MMAs per line: S (phase A), per chunk dP += dO V^T then
+// Per line the ring carries  Q K (V_n dO_n)* Q K ; item g lives in load slot g % kNLd (fp32: converted in place), so the
+// loads and conversions of the next chunks overlap the MMAs of the current one.  MMAs per line: S (phase A), per chunk dP += dO V^T then
 // dV = P^T dO (phase B; the V buffer is released right after the dP MMAs), dS by the P/dS group (phase C),
 // dQ = dS K and dK = dS^T Q (phase D).
 template <int LK, bool BF>
@@ -87,9 +89,10 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
     const int nk = (total_lines - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (tid == 0) {
-        for (int i = 0; i < kNLd; ++i) { mbar_init(&bars[B_LD_FULL + i], 1); mbar_init(&bars[B_LD_EMPTY + i], BF ? 1 : kConvThreads); }
+        for (int i = 0; i < kNLd; ++i) {
+            mbar_init(&bars[B_LD_FULL + i], 1); mbar_init(&bars[B_LD_EMPTY + i], 1); mbar_init(&bars[B_OP_FULL + i], kConvThreads);
+        }
         for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_O_FULL + i], 1); mbar_init(&bars[B_O_EMPTY + i], 128); }
-        for (int i = 0; i < kNOp; ++i) { mbar_init(&bars[B_OP_FULL + i], kConvThreads); mbar_init(&bars[B_OP_EMPTY + i], 1); }
         mbar_init(&bars[B_OUT_FULL], 1); mbar_init(&bars[B_STAGED], 128);
         for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_S_FULL + i], 1); mbar_init(&bars[B_S_EMPTY + i], 128); }
         mbar_init(&bars[B_P_FULL], 128); mbar_init(&bars[B_P_EMPTY], 1);
@@ -108,6 +111,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
     auto line_coords = [&](int line, int &cw, int &ch, int &cb) {
         cb = line / p.NL;
         const int i = line - cb * p.NL;
+        if (!p.col) cb = p.B - 1 - cb;      // second pass: samples backwards (the tail of the column pass is still in L2)
         if (p.col) { cw = i; ch = 0; } else { cw = 0; ch = i; }
     };
     // output item i of a line: i < NCH -> dV chunk i; NCH -> dQ; NCH+1 -> dK
@@ -121,16 +125,19 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
             if (lane == 0) {
                 uint32_t g = 0;
                 int dbg_n = 0;
+                const uint64_t pol_keep = p.hints ? l2_policy_evict_last() : l2_policy_evict_normal();
+                const uint64_t pol_stream = p.hints ? l2_policy_evict_first() : l2_policy_evict_normal();
                 auto emit = [&](const CUtensorMap *m, int c0, int line) {
                     int cw, ch, cb;
                     line_coords(line, cw, ch, cb);
+                    const uint64_t pol = p.col && cb >= p.keep_from ? pol_keep : pol_stream;
                     const int slot = g % kNLd;
                     mbar_wait(&bars[B_LD_EMPTY + slot], ((g / kNLd) & 1) ^ 1);
                     CCA_STAMP(0);
                     uint8_t *dst = smem + S::off_ld + slot * T::kSlot;
                     mbar_expect_tx(&bars[B_LD_FULL + slot], T::kSlot);
-                    tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, cb);
-                    if constexpr (!BF) tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, cb);
+                    tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, cb, pol);
+                    if constexpr (!BF) tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, cb, pol);
                     ++g;
                 };
                 // ring:  Q0 K0 | (V dO)* Q1 K1 Q0 K0 | (V dO)* Q2 K2 Q1 K1 | ...   (S of the next line is issued while the
@@ -149,23 +156,17 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
             const uint32_t id_kk_s = instr_desc(kFmtBF16, kFmtBF16, 128, LK, false, false);    // S, dP : K-major x K-major, N = LK
             const uint32_t id_mn_mn = instr_desc(kFmtBF16, kFmtBF16, 128, kNC, true, true);    // dV, dK: A^T planes x channel planes
             const uint32_t id_k_mn = instr_desc(kFmtBF16, kFmtBF16, 128, kNC, false, true);    // dQ
-            const uint32_t op_base = smem_u32(smem + S::off_op), pb = smem_u32(smem + S::off_p);
+            const uint32_t pb = smem_u32(smem + S::off_p);
             const uint32_t LO8 = 8 * T::kPlane, LOP = T::kPP * T::kPlane;
             uint32_t u = 0, oc = 0;
             int dbg_n = lane == 0 ? 0 : 512;
-            // operand sources: fp32 -> converted planes (item g -> operand buffer g % 3, K-major / MN-major by descriptor);
-            //                  bf16 -> the TMA tile of item g itself (load slot g % kNLd) read with SWIZZLE_128B descriptors:
+            // operand of ring item g = load slot g % kNLd: fp32 -> bf16 hi/lo planes written in place (K-major / MN-major by descriptor);
+            //                  bf16 -> the TMA tile itself read with SWIZZLE_128B descriptors:
             //                          K-major use: k-step = +32 B; MN-major use: k-step = +2048 B (16 pixel rows)
             const uint32_t ld_base = smem_u32(smem + S::off_ld);
-            auto opb = [&](uint32_t g) { return BF ? ld_base + (g % kNLd) * T::kSlot : op_base + (g % kNOp) * T::kOp; };
-            auto wait_op = [&](uint32_t g) {
-                if constexpr (BF) mbar_wait(&bars[B_LD_FULL + g % kNLd], (g / kNLd) & 1);
-                else mbar_wait(&bars[B_OP_FULL + g % kNOp], (g / kNOp) & 1);
-            };
-            auto free_op = [&](uint32_t g) {
-                if constexpr (BF) commit_to(&bars[B_LD_EMPTY + g % kNLd]);
-                else commit_to(&bars[B_OP_EMPTY + g % kNOp]);
-            };
+            auto opb = [&](uint32_t g) { return ld_base + (g % kNLd) * T::kSlot; };
+            auto wait_op = [&](uint32_t g) { mbar_wait(&bars[(BF ? B_LD_FULL : B_OP_FULL) + g % kNLd], (g / kNLd) & 1); };
+            auto free_op = [&](uint32_t g) { commit_to(&bars[B_LD_EMPTY + g % kNLd]); };
             // channel-tile operand parameters: (k-step, lbo, sbo, layout) when the contraction runs over channels (kmaj) or
             // over pixels (mnmaj)
             constexpr uint32_t KS_K = BF ? 32 : 2 * T::kPlane, LBO_K = BF ? 16 : T::kPlane, SBO_K = BF ? 1024 : 128;
@@ -240,6 +241,8 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
             if (lane == 0) {
                 const uint32_t total = (uint32_t)nk * NO;
                 uint8_t *slot = smem + S::off_out;
+                const uint64_t pol_keep = p.hints ? l2_policy_evict_last() : l2_policy_evict_normal();
+                const uint64_t pol_stream = p.hints ? l2_policy_evict_first() : l2_policy_evict_normal();
                 for (uint32_t c = 0; c < total; ++c) {
                     const int k = c / NO, i = c - k * NO;
                     int cw, ch, cb;
@@ -249,11 +252,12 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                     mbar_arrive(&bars[B_OUT_FULL]);
                     mbar_wait(&bars[B_STAGED], c & 1);
                     if (p.col) {                                   // column pass defines dq/dk/dv ...
-                        tma_store_4d(out_map(i), slot, out_c0(i), cw, ch, cb);
-                        if constexpr (!BF) tma_store_4d(out_map(i), slot + T::kTile, out_c0(i) + 32, cw, ch, cb);
+                        const uint64_t pol = cb >= p.keep_from ? pol_keep : pol_stream;
+                        tma_store_4d(out_map(i), slot, out_c0(i), cw, ch, cb, pol);
+                        if constexpr (!BF) tma_store_4d(out_map(i), slot + T::kTile, out_c0(i) + 32, cw, ch, cb, pol);
                     } else {                                       // ... the row pass accumulates onto them (TMA reduce-add at L2)
-                        tma_reduce_add_4d(out_map(i), slot, out_c0(i), cw, ch, cb);
-                        if constexpr (!BF) tma_reduce_add_4d(out_map(i), slot + T::kTile, out_c0(i) + 32, cw, ch, cb);
+                        tma_reduce_add_4d(out_map(i), slot, out_c0(i), cw, ch, cb, pol_stream);
+                        if constexpr (!BF) tma_reduce_add_4d(out_map(i), slot + T::kTile, out_c0(i) + 32, cw, ch, cb, pol_stream);
                     }
                     tma_store_commit();
                 }
@@ -262,20 +266,17 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
         }
     } else if (warp >= kWarpConv0) {
         // =============================== converters (256 threads) ===============================
-        reg_dec<kRegsConv>();
+        reg_dec<kRegsConvB>();
         const int t = tid - kWarpConv0 * 32;
         const uint32_t total = BF ? 0u : (uint32_t)nk * NI;         // bf16 tiles need no conversion
         int dbg_n = t == 0 ? 0 : 512;
         for (uint32_t g = 0; g < total; ++g) {
-            const int slot = g % kNLd, ob = g % kNOp;
+            const int slot = g % kNLd;
             mbar_wait(&bars[B_LD_FULL + slot], (g / kNLd) & 1);
             CCA_STAMP(1);
-            mbar_wait(&bars[B_OP_EMPTY + ob], ((g / kNOp) & 1) ^ 1);
-            CCA_STAMP(1);
-            convert_slot<LK, BF>(smem + S::off_ld + slot * T::kSlot, smem + S::off_op + ob * T::kOp, t);
+            if constexpr (!BF) convert_slot_inplace<LK>(smem + S::off_ld + slot * T::kSlot, t);
             fence_proxy_async();
-            mbar_arrive(&bars[B_OP_FULL + ob]);
-            mbar_arrive(&bars[B_LD_EMPTY + slot]);
+            mbar_arrive(&bars[B_OP_FULL + slot]);
             CCA_STAMP(1);
         }
     } else if (warp >= 4) {
@@ -484,6 +485,13 @@ cudaError_t launch_bwd_pass(const void *dout, const void *q, const void *k, cons
     p.B = d.B; p.H = d.H; p.W = d.W; p.C = d.C; p.Cq = d.Cq;
     p.L = col ? d.H : d.W; p.NL = col ? d.W : d.H; p.col = col ? 1 : 0;
     p.lse = lse; p.delta = delta;
+    {   // per sample the row pass re-reads q,k,v,dout and accumulates onto dq,dk,dv
+        const double per_sample = (4.0 * d.Cq + 3.0 * d.C) * d.H * d.W * (BF ? 2 : 4);
+        int keep = (int)(tc_l2_keep_mb() * 1e6 / per_sample);
+        if (keep > d.B) keep = d.B;
+        p.hints = tc_l2_hints();
+        p.keep_from = d.B - keep;
+    }
     p.dbg = g_bwd_dbg ? g_bwd_dbg + (col ? 0 : 2560) : nullptr;
     auto kern = cca_tc_bwd_kernel<LK, BF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<LK, BF>::kBytes);

@@ -54,6 +54,8 @@ struct FwdParams {
     float2 *stats;         // [B,H,W] (m_c, l_c) of the column branch
     float *lse;            // [B,H,W]
     unsigned int *done;    // [B] column lines completed (MODE_FUSED only)
+    int hints;             // L2 eviction hints on the bulk copies: column lines of samples >= keep_from are kept (evict_last:
+    int keep_from;         // the row pass, which walks the samples backwards, finds them in L2), everything else streams
     long long *dbg;        // optional timeline buffer (4 roles x 512 stamps), CTA 0 only; nullptr in production
 };
 
@@ -83,6 +85,9 @@ __device__ __forceinline__ Item decode_item(const FwdParams &p, int idx)
         const int nl = it.col ? p.W : p.H;
         it.b = idx / nl;
         it.i = idx - it.b * nl;
+        // the row pass walks the samples backwards: what the column pass touched last (v, q, k and the partial output of
+        // the last samples) is still in L2 when the row pass starts
+        if (!it.col) it.b = p.B - 1 - it.b;
     }
     it.L = it.col ? p.H : p.W;
     return it;
@@ -208,16 +213,23 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             if (lane == 0) {
                 uint32_t g = 0;
                 int dbg_n = 0;
+                const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
                 auto emit = [&](const CUtensorMap *mc, const CUtensorMap *mr, int c0, const Item &it) {
                     const CUtensorMap *m = it.col ? mc : mr;
+                    const uint64_t pol = it.col && it.b >= p.keep_from ? pol_keep : pol_stream;
                     const int cw = it.col ? it.i : 0, ch = it.col ? 0 : it.i;
                     const int slot = g % kNLd;
                     mbar_wait(&bars[B_LD_EMPTY + slot], ((g / kNLd) & 1) ^ 1);
                     CCA_STAMP(0);
                     uint8_t *dst = smem + S::off_ld + slot * T::kSlot;
                     mbar_expect_tx(&bars[B_LD_FULL + slot], T::kSlot);
-                    tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, it.b);
-                    if constexpr (!BF) tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, it.b);
+                    if (p.hints) {
+                        tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, it.b, pol);
+                        if constexpr (!BF) tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, it.b, pol);
+                    } else {
+                        tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, it.b);
+                        if constexpr (!BF) tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, it.b);
+                    }
                     ++g;
                 };
                 // ---- scheduler: hand out the next line of this CTA
@@ -383,6 +395,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             // Column items are published (per-sample counter) after their last store has completed.
             if (lane == 0) {
                 uint32_t prep = 0;                         // chunks prepared so far (chunk c belongs to item c / NCH)
+                const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
                 int pub_k = 0;                             // items [0, pub_k) are published / need no publishing
                 // a row chunk must not wait for a column item this warp has yet to publish (static fused order only:
                 // the dynamic scheduler hands out a row line only after all column lines of its sample were published)
@@ -402,8 +415,13 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                     if (p.mode <= MODE_DYNAMIC) { wait_done(p.done + it.b, (unsigned)p.W); fence_proxy_async_all(); }
                     uint8_t *dst = smem + S::off_out + os * T::kSlot;
                     mbar_expect_tx(&bars[B_OUT_FULL + os], T::kSlot);
-                    tma_load_4d(dst, &mor, &bars[B_OUT_FULL + os], n * kNC, 0, it.i, it.b);
-                    if constexpr (!BF) tma_load_4d(dst + T::kTile, &mor, &bars[B_OUT_FULL + os], n * kNC + 32, 0, it.i, it.b);
+                    if (p.hints) {                                 // the partial is read exactly once
+                        tma_load_4d(dst, &mor, &bars[B_OUT_FULL + os], n * kNC, 0, it.i, it.b, pol_stream);
+                        if constexpr (!BF) tma_load_4d(dst + T::kTile, &mor, &bars[B_OUT_FULL + os], n * kNC + 32, 0, it.i, it.b, pol_stream);
+                    } else {
+                        tma_load_4d(dst, &mor, &bars[B_OUT_FULL + os], n * kNC, 0, it.i, it.b);
+                        if constexpr (!BF) tma_load_4d(dst + T::kTile, &mor, &bars[B_OUT_FULL + os], n * kNC + 32, 0, it.i, it.b);
+                    }
                 };
                 Item it;
                 for (int k = 0; get_item(k, it); ++k) {
@@ -421,8 +439,14 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                         }
                         mbar_wait(&bars[B_STAGED + os], (c / kNOut) & 1);
                         const uint8_t *slot = smem + S::off_out + os * T::kSlot;
-                        tma_store_4d(mo, slot, n * kNC, cw, ch, it.b);
-                        if constexpr (!BF) tma_store_4d(mo, slot + T::kTile, n * kNC + 32, cw, ch, it.b);
+                        if (p.hints) {
+                            const uint64_t pol = it.col && it.b >= p.keep_from ? pol_keep : pol_stream;
+                            tma_store_4d(mo, slot, n * kNC, cw, ch, it.b, pol);
+                            if constexpr (!BF) tma_store_4d(mo, slot + T::kTile, n * kNC + 32, cw, ch, it.b, pol);
+                        } else {
+                            tma_store_4d(mo, slot, n * kNC, cw, ch, it.b);
+                            if constexpr (!BF) tma_store_4d(mo, slot + T::kTile, n * kNC + 32, cw, ch, it.b);
+                        }
                         tma_store_commit();
                         if (n == NCH - 1) {
                             if (it.col && p.mode <= MODE_DYNAMIC) {
@@ -434,11 +458,14 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                             }
                             pub_k = k + 1;
                         }
-                        // keep two chunks prepared ahead; slot of chunk c+2 was last used by chunk c-1, whose store must have drained
-                        while (prep <= c + 2 && can_prepare(prep)) {
+                        // keep the ring of kNOut slots full: chunk c+kNOut reuses the slot of the store just issued, as soon as
+                        // that store has been read out of shared memory (a few hundred cycles; this lane has nothing else to do
+                        // until the next chunk is staged).  The partial of a row item is thus in flight two full chunk periods
+                        // before the epilogue needs it -- one period did not cover the L2 latency of the tile.
+                        while (prep <= c + kNOut && can_prepare(prep)) {
                             Item pi;
                             try_item((int)(prep / NCH), pi);
-                            tma_store_wait_read<1>();
+                            if (prep == c + kNOut) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
                             prepare(prep, pi);
                             ++prep;
                         }
@@ -677,6 +704,13 @@ cudaError_t launch_fwd(const void *q, const void *k, const void *v, void *out, f
     p.B = d.B; p.H = d.H; p.W = d.W; p.C = d.C; p.Cq = d.Cq;
     p.mode = mode; p.stats = stats; p.lse = lse; p.sched = cnt; p.done = cnt + 2; p.rown = cnt + 2 + d.B;
     p.dbg = g_dbg ? g_dbg + (mode == MODE_ROW_ONLY ? 2560 : 0) : nullptr;
+    // L2 residency: keep (evict_last) what the column pass touches for its last samples -- as many as fit the budget --
+    // because the row pass starts with exactly those; everything else is marked evict_first
+    const double per_sample = (2.0 * d.Cq + 2.0 * d.C) * d.H * d.W * (BF ? 2 : 4);
+    int keep = (int)(tc_l2_keep_mb() * 1e6 / per_sample);
+    if (keep > d.B) keep = d.B;
+    p.hints = tc_l2_hints();
+    p.keep_from = mode <= MODE_DYNAMIC ? 0 : d.B - keep;
     auto kern = cca_tc_fwd_kernel<LK, BF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem<LK, BF>::kBytes);
     if (e != cudaSuccess) return e;

@@ -14,6 +14,10 @@ for _ in range(3):
 buf = torch.zeros(2 * 5 * 512, dtype=torch.int64, device=dev)
 fn = lib.cca_b200__set_debug_buffer
 fn.argtypes = [ctypes.c_void_p]; fn.restype = None
+tp = lib.cca_b200__set_two_pass; tp.argtypes = [ctypes.c_int]; tp.restype = None
+tp(int(sys.argv[1]) if len(sys.argv) > 1 else 1)        # 1: two launches (default), 2: static fused, 0: dynamic fused
+for _ in range(2):
+    cca_forward(q, k, v, impl="tc")
 fn(buf.data_ptr())
 cca_forward(q, k, v, impl="tc")
 torch.cuda.synchronize()
@@ -27,7 +31,6 @@ def timeit(tag):
     for _ in range(20): cca_forward(q, k, v, impl="tc")
     e1.record(); torch.cuda.synchronize()
     print(tag, "fwd ms", e0.elapsed_time(e1) / 20)
-tp = lib.cca_b200__set_two_pass; tp.argtypes = [ctypes.c_int]; tp.restype = None
 tp(0); timeit("one launch, dynamic :")
 tp(2); timeit("one launch, static  :")
 tp(1); timeit("two launches        :")
@@ -42,4 +45,4 @@ for ps, pname in enumerate(["FUSED / COLUMN pass", "ROW pass"]):
     for role in range(5):
         st = [int(x) - base for x in t[ps, role] if x > 0]
         print(f"--- {names[role]}: {len(st)} stamps")
-        print(" ".join(str(x) for x in st[:70]))
+        print(" ".join(str(x) for x in st))
