@@ -47,6 +47,16 @@ int tc_l2_hints()
 }
 double tc_l2_keep_mb() { tc_l2_hints(); return g_l2_keep_mb; }
 void set_tc_l2_hints(int on, double keep_mb) { g_l2_hints = on != 0; g_l2_keep_mb = keep_mb; }
+static int g_pdl = -1;
+int tc_pdl()
+{
+    if (g_pdl < 0) {
+        const char *e = getenv("CCA_B200_PDL");
+        g_pdl = e ? (atoi(e) != 0) : 1;
+    }
+    return g_pdl;
+}
+void set_tc_pdl(int on) { g_pdl = on != 0; }
 }  // namespace cca
 
 using namespace cca;
@@ -61,6 +71,7 @@ CCA_API void cca_b200__set_two_pass(int on) { set_tc_two_pass(on); }
 CCA_API void cca_b200__set_bwd_debug_buffer(void *p) { set_tc_bwd_debug_buffer(p); }
 // A/B aid: L2 eviction hints on / off and the evict_last budget in MB
 CCA_API void cca_b200__set_l2_hints(int on, double keep_mb) { set_tc_l2_hints(on, keep_mb); }
+CCA_API void cca_b200__set_pdl(int on) { set_tc_pdl(on); }
 const char *cca_b200_last_error(void) { return g_err; }
 const char *cca_b200_strerror(int s)
 {

@@ -55,5 +55,8 @@ void set_tc_bwd_debug_buffer(void *p);
 int tc_l2_hints();
 double tc_l2_keep_mb();
 void set_tc_l2_hints(int on, double keep_mb);
+// programmatic dependent launch between the passes of one op (CCA_B200_PDL = 0/1, default 1)
+int tc_pdl();
+void set_tc_pdl(int on);
 
 }  // namespace cca

@@ -106,6 +106,10 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // Programmatic dependent launch: the column pass is launched behind the delta kernel and the row pass behind the column
+    // pass, each without waiting for its predecessor to finish.  Only two places touch what the predecessor produces: the
+    // P/dS group reads delta (column pass <- delta kernel), the store warp accumulates onto dq/dk/dv (row pass <- column pass).
+    pdl_launch_dependents();
 
     auto line_of = [&](int k) { return (int)blockIdx.x + k * (int)gridDim.x; };
     auto line_coords = [&](int line, int &cw, int &ch, int &cb) {
@@ -251,6 +255,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                     tma_store_wait_read<0>();
                     mbar_arrive(&bars[B_OUT_FULL]);
                     mbar_wait(&bars[B_STAGED], c & 1);
+                    if (c == 0) pdl_wait();
                     if (p.col) {                                   // column pass defines dq/dk/dv ...
                         const uint64_t pol = cb >= p.keep_from ? pol_keep : pol_stream;
                         tma_store_4d(out_map(i), slot, out_c0(i), cw, ch, cb, pol);
@@ -293,6 +298,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
             if (rvalid) {
                 const long pix = p.col ? ((long)cb * p.H + r) * p.W + cw : ((long)cb * p.H + ch) * p.W + r;
                 lse2 = p.lse[pix] * kLog2e;
+                if (p.col) pdl_wait();                 // delta comes from the kernel right before the column pass
                 dl = p.delta[pix];
             }
             uint8_t *ph = smem + S::off_p + r * 16, *pl = ph + T::kPP * T::kPlane;
@@ -304,12 +310,16 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
             CCA_STAMP(3);
             // both phases stream the TMEM row 16 columns at a time (small loops: the instruction footprint of a fully
             // unrolled LK-element register array cost more than the extra tcgen05.wait::ld round trips)
+            float nx[16];                                      // next 16 columns, in flight while the current ones are processed
+            tmem_ld16(tsd, reinterpret_cast<uint32_t *>(nx));
             mbar_wait(&bars[B_P_EMPTY], (k & 1) ^ 1);
-#pragma unroll 1
+#pragma unroll
             for (int c0 = 0; c0 < LK; c0 += 16) {
                 float s[16];
-                tmem_ld16(tsd + c0, reinterpret_cast<uint32_t *>(s));
-                tmem_ld_wait();
+                tmem_ld_wait16(reinterpret_cast<uint32_t *>(nx));
+#pragma unroll
+                for (int e = 0; e < 16; ++e) s[e] = nx[e];
+                if (c0 + 16 < LK) tmem_ld16(tsd + c0 + 16, reinterpret_cast<uint32_t *>(nx));
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
                     const int j = c0 + e;
@@ -341,11 +351,14 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
             mbar_wait(&bars[B_DP_FULL], k & 1);
             tc_fence_after();
             CCA_STAMP(3);
-#pragma unroll 1
+            tmem_ld16(tsd, reinterpret_cast<uint32_t *>(nx));
+#pragma unroll
             for (int c0 = 0; c0 < LK; c0 += 16) {
                 float dp[16];
-                tmem_ld16(tsd + c0, reinterpret_cast<uint32_t *>(dp));
-                tmem_ld_wait();
+                tmem_ld_wait16(reinterpret_cast<uint32_t *>(nx));
+#pragma unroll
+                for (int e = 0; e < 16; ++e) dp[e] = nx[e];
+                if (c0 + 16 < LK) tmem_ld16(tsd + c0 + 16, reinterpret_cast<uint32_t *>(nx));
                 if (r < LK) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -432,8 +445,10 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
 __global__ void __launch_bounds__(256) cca_delta_nhwc_kernel(const float4 *__restrict__ dout, const float4 *__restrict__ out,
                                                              float *__restrict__ delta, long npix, int c4)
 {
-    const long pix = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (pix >= npix) return;
+    // pixels are walked backwards: the column pass starts with sample 0, whose dout is then the most recent data in L2
+    pdl_launch_dependents();
+    const long pix = npix - 1 - ((long)blockIdx.x * 8 + (threadIdx.x >> 5));
+    if (pix < 0) return;
     const int lane = threadIdx.x & 31;
     const float4 *a = dout + pix * c4, *b = out + pix * c4;
     float s = 0.f;
@@ -450,8 +465,9 @@ __global__ void __launch_bounds__(256) cca_delta_nhwc_kernel(const float4 *__res
 __global__ void __launch_bounds__(256) cca_delta_nhwc_bf16_kernel(const uint4 *__restrict__ dout, const uint4 *__restrict__ out,
                                                                   float *__restrict__ delta, long npix, int c8)
 {
-    const long pix = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (pix >= npix) return;
+    pdl_launch_dependents();
+    const long pix = npix - 1 - ((long)blockIdx.x * 8 + (threadIdx.x >> 5));
+    if (pix < 0) return;
     const int lane = threadIdx.x & 31;
     const uint4 *a = dout + pix * c8, *b = out + pix * c8;
     float s = 0.f;
@@ -498,9 +514,16 @@ cudaError_t launch_bwd_pass(const void *dout, const void *q, const void *k, cons
     if (e != cudaSuccess) return e;
     const int lines = d.B * p.NL;
     const int grid = lines < sm_count() ? lines : sm_count();
-    kern<<<grid, kThreads, BwdSmem<LK, BF>::kBytes, st>>>(mq, mk, mv, mdo, mdq, mdk, mdv, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = BwdSmem<LK, BF>::kBytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = tc_pdl() ? 1 : 0;
+    e = cudaLaunchKernelEx(&cfg, kern, mq, mk, mv, mdo, mdq, mdk, mdv, p);
     count_launch();
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace

@@ -184,6 +184,10 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // Programmatic dependent launch: the row pass is launched while the column pass is still draining; its CTAs load q,k,v,
+    // compute S, the row softmax and the first P V products right away and only wait (pdl_wait) where they first touch what
+    // the column pass produces: the column statistics (softmax group) and the partial output (store warp).
+    pdl_launch_dependents();
 
     // ---- item records (see Rec): blocking / non-blocking readers used by every role
     auto rec_item = [&](const Rec &r) { Item it; it.col = r.col; it.b = r.b; it.i = r.i; it.L = r.col ? p.H : p.W; return it; };
@@ -413,6 +417,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                     const int n = c % NCH, os = c % kNOut;
                     if (it.col) { mbar_arrive(&bars[B_OUT_FULL + os]); return; }
                     if (p.mode <= MODE_DYNAMIC) { wait_done(p.done + it.b, (unsigned)p.W); fence_proxy_async_all(); }
+                    pdl_wait();                                // (row pass launched ahead of the column pass's completion)
                     uint8_t *dst = smem + S::off_out + os * T::kSlot;
                     mbar_expect_tx(&bars[B_OUT_FULL + os], T::kSlot);
                     if (p.hints) {                                 // the partial is read exactly once
@@ -574,6 +579,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             // ---- per-pixel statistics / merge scales (off the MMA's critical path now)
             float sa = 0.f, sb = 0.f;
             if (!it.col && p.mode <= MODE_DYNAMIC) wait_done(p.done + it.b, (unsigned)p.W);   // column stats of this sample complete
+            if (!it.col) pdl_wait();                           // row pass launched ahead of the column pass's completion
             if (rvalid) {
                 const long pix = it.col ? ((long)it.b * p.H + r) * p.W + it.i : ((long)it.b * p.H + it.i) * p.W + r;
                 const float mn = m * kLn2;                       // natural-log units
@@ -716,9 +722,16 @@ cudaError_t launch_fwd(const void *q, const void *k, const void *v, void *out, f
     if (e != cudaSuccess) return e;
     const int items = mode <= MODE_DYNAMIC ? d.B * (d.W + d.H) : (mode == MODE_COL_ONLY ? d.B * d.W : d.B * d.H);
     const int grid = items < sm_count() ? items : sm_count();
-    kern<<<grid, kThreads, FwdSmem<LK, BF>::kBytes, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = FwdSmem<LK, BF>::kBytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (mode == MODE_ROW_ONLY && tc_pdl()) ? 1 : 0;     // only the row pass may start ahead of its predecessor
+    e = cudaLaunchKernelEx(&cfg, kern, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], p);
     count_launch();
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 // Launch policy of the forward (CCA_B200_FUSED): 0 = two launches (column pass, row pass); 1 = ONE launch with dynamic
