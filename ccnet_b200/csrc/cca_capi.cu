@@ -52,11 +52,12 @@ int tc_pdl()
 {
     if (g_pdl < 0) {
         const char *e = getenv("CCA_B200_PDL");
-        g_pdl = e ? (atoi(e) != 0) : 1;
+        g_pdl = e ? atoi(e) : 1;           // 0: off, 1: dependent launch, 2: + overlapped second pass (per-sample counters)
+        if (g_pdl < 0 || g_pdl > 2) g_pdl = 1;
     }
     return g_pdl;
 }
-void set_tc_pdl(int on) { g_pdl = on != 0; }
+void set_tc_pdl(int on) { g_pdl = on < 0 || on > 2 ? 1 : on; }
 }  // namespace cca
 
 using namespace cca;

@@ -33,6 +33,9 @@ static_assert(reg_pool_ok(kRegsSoft, kRegsEpi, kRegsConvB), "setmaxnreg pool");
 struct BwdParams {
     int B, H, W, C, Cq;
     int L, NL, col;
+    int sync;              // 1: the row pass runs overlapped with the tail of the column pass (programmatic dependent launch);
+    unsigned int *done;    // done[b] counts the column lines of sample b whose dq/dk/dv stores are complete, and a row line
+                           // only waits for the column lines of its own sample before it accumulates onto them
     int hints, keep_from;  // L2 eviction hints: the column pass keeps (evict_last) the lines of samples >= keep_from for the row
                            // pass, which walks the samples backwards; everything else streams (evict_first)
     const float *lse;
@@ -44,6 +47,18 @@ struct BwdParams {
     do {                                                                                         \
         if (p.dbg && blockIdx.x == 0 && dbg_n < 512) p.dbg[(role) * 512 + dbg_n++] = clock64();  \
     } while (0)
+
+__device__ __forceinline__ void wait_count(const unsigned int *cnt, unsigned int need)
+{
+    unsigned int spins = 0, v;
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+        if (v >= need) return;
+        __nanosleep(64);
+        if (++spins > (1u << 24)) __trap();      // a broken dependency chain traps instead of hanging the GPU
+    }
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 template <int LK, bool BF> struct BwdSmem {
     using T = Tiles<LK, BF>;
@@ -115,7 +130,9 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
     auto line_coords = [&](int line, int &cw, int &ch, int &cb) {
         cb = line / p.NL;
         const int i = line - cb * p.NL;
-        if (!p.col) cb = p.B - 1 - cb;      // second pass: samples backwards (the tail of the column pass is still in L2)
+        // second pass: samples backwards (the tail of the column pass is still in L2) -- unless it overlaps the column pass,
+        // whose first samples are complete first
+        if (!p.col && !p.sync) cb = p.B - 1 - cb;
         if (p.col) { cw = i; ch = 0; } else { cw = 0; ch = i; }
     };
     // output item i of a line: i < NCH -> dV chunk i; NCH -> dQ; NCH+1 -> dK
@@ -255,7 +272,12 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                     tma_store_wait_read<0>();
                     mbar_arrive(&bars[B_OUT_FULL]);
                     mbar_wait(&bars[B_STAGED], c & 1);
-                    if (c == 0) pdl_wait();
+                    if (p.sync && !p.col) {
+                        // overlapped row pass: all column lines of this sample must have landed before we accumulate
+                        if (i == 0) { wait_count(p.done + cb, (unsigned)p.W); fence_proxy_async_global(); }
+                    } else if (c == 0) {
+                        pdl_wait();
+                    }
                     if (p.col) {                                   // column pass defines dq/dk/dv ...
                         const uint64_t pol = cb >= p.keep_from ? pol_keep : pol_stream;
                         tma_store_4d(out_map(i), slot, out_c0(i), cw, ch, cb, pol);
@@ -265,8 +287,25 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                         if constexpr (!BF) tma_reduce_add_4d(out_map(i), slot + T::kTile, out_c0(i) + 32, cw, ch, cb, pol_stream);
                     }
                     tma_store_commit();
+                    if (p.sync && p.col && i == 0 && k > 0) {
+                        // publish the previous line: its stores were committed at least one chunk period ago, so waiting for
+                        // everything but the group just committed costs (almost) nothing
+                        int pw, ph2, pb;
+                        line_coords(line_of(k - 1), pw, ph2, pb);
+                        tma_store_wait_all<1>();
+                        fence_proxy_async_global();
+                        __threadfence();
+                        atomicAdd(p.done + pb, 1u);
+                    }
                 }
                 tma_store_wait_all<0>();
+                if (p.sync && p.col && nk > 0) {
+                    int pw, ph2, pb;
+                    line_coords(line_of(nk - 1), pw, ph2, pb);
+                    fence_proxy_async_global();
+                    __threadfence();
+                    atomicAdd(p.done + pb, 1u);
+                }
             }
         }
     } else if (warp >= kWarpConv0) {
@@ -486,7 +525,8 @@ long long *g_bwd_dbg = nullptr;
 
 template <int LK, bool BF>
 cudaError_t launch_bwd_pass(const void *dout, const void *q, const void *k, const void *v, const float *lse, const float *delta,
-                            void *dq, void *dk, void *dv, Dims d, bool col, cudaStream_t st, const char **why)
+                            void *dq, void *dk, void *dv, unsigned int *done, int sync, Dims d, bool col, cudaStream_t st,
+                            const char **why)
 {
     CUtensorMap mq, mk, mv, mdo, mdq, mdk, mdv;
     const bool ok = make_map(&mq, q, d.B, d.H, d.W, d.Cq, LK, col, BF) && make_map(&mk, k, d.B, d.H, d.W, d.Cq, LK, col, BF) &&
@@ -501,6 +541,7 @@ cudaError_t launch_bwd_pass(const void *dout, const void *q, const void *k, cons
     p.B = d.B; p.H = d.H; p.W = d.W; p.C = d.C; p.Cq = d.Cq;
     p.L = col ? d.H : d.W; p.NL = col ? d.W : d.H; p.col = col ? 1 : 0;
     p.lse = lse; p.delta = delta;
+    p.done = done; p.sync = sync;
     {   // per sample the row pass re-reads q,k,v,dout and accumulates onto dq,dk,dv
         const double per_sample = (4.0 * d.Cq + 3.0 * d.C) * d.H * d.W * (BF ? 2 : 4);
         int keep = (int)(tc_l2_keep_mb() * 1e6 / per_sample);
@@ -540,6 +581,13 @@ cudaError_t tc_backward(const void *dout, const void *q, const void *k, const vo
     const long npix = (long)d.B * d.H * d.W;
     const bool bf = dtype == CCA_BF16;
     const unsigned dgrid = (unsigned)((npix + 7) / 8);
+    // tc_pdl() == 2: the row pass overlaps the tail of the column pass; per-sample completion counters (behind delta in ws)
+    unsigned int *done = reinterpret_cast<unsigned int *>(delta + npix);
+    const int sync = tc_pdl() == 2 ? 1 : 0;
+    if (sync) {
+        cudaError_t e0 = cudaMemsetAsync(done, 0, sizeof(unsigned int) * d.B, st);
+        if (e0 != cudaSuccess) return e0;
+    }
     if (bf)
         cca_delta_nhwc_bf16_kernel<<<dgrid, 256, 0, st>>>(reinterpret_cast<const uint4 *>(dout), reinterpret_cast<const uint4 *>(out),
                                                           delta, npix, d.C / 8);
@@ -551,10 +599,10 @@ cudaError_t tc_backward(const void *dout, const void *q, const void *k, const vo
     if (e != cudaSuccess) return e;
     auto go = [&](int lk, bool col) {
         if (bf)
-            return lk == 80 ? launch_bwd_pass<80, true>(dout, q, k, v, lse, delta, dq, dk, dv, d, col, st, why)
-                            : launch_bwd_pass<112, true>(dout, q, k, v, lse, delta, dq, dk, dv, d, col, st, why);
-        return lk == 80 ? launch_bwd_pass<80, false>(dout, q, k, v, lse, delta, dq, dk, dv, d, col, st, why)
-                        : launch_bwd_pass<112, false>(dout, q, k, v, lse, delta, dq, dk, dv, d, col, st, why);
+            return lk == 80 ? launch_bwd_pass<80, true>(dout, q, k, v, lse, delta, dq, dk, dv, done, sync, d, col, st, why)
+                            : launch_bwd_pass<112, true>(dout, q, k, v, lse, delta, dq, dk, dv, done, sync, d, col, st, why);
+        return lk == 80 ? launch_bwd_pass<80, false>(dout, q, k, v, lse, delta, dq, dk, dv, done, sync, d, col, st, why)
+                        : launch_bwd_pass<112, false>(dout, q, k, v, lse, delta, dq, dk, dv, done, sync, d, col, st, why);
     };
     e = go(lk_for(d.H), true);
     if (e != cudaSuccess) return e;

@@ -54,6 +54,8 @@ struct FwdParams {
     float2 *stats;         // [B,H,W] (m_c, l_c) of the column branch
     float *lse;            // [B,H,W]
     unsigned int *done;    // [B] column lines completed (MODE_FUSED only)
+    int sync;              // two launches, the row pass overlapping the tail of the column pass (programmatic dependent launch):
+                           // column lines are counted in done[] as in the fused modes and a row line waits for its own sample only
     int hints;             // L2 eviction hints on the bulk copies: column lines of samples >= keep_from are kept (evict_last:
     int keep_from;         // the row pass, which walks the samples backwards, finds them in L2), everything else streams
     long long *dbg;        // optional timeline buffer (4 roles x 512 stamps), CTA 0 only; nullptr in production
@@ -87,7 +89,7 @@ __device__ __forceinline__ Item decode_item(const FwdParams &p, int idx)
         it.i = idx - it.b * nl;
         // the row pass walks the samples backwards: what the column pass touched last (v, q, k and the partial output of
         // the last samples) is still in L2 when the row pass starts
-        if (!it.col) it.b = p.B - 1 - it.b;
+        if (!it.col && !p.sync) it.b = p.B - 1 - it.b;       // (an overlapped row pass starts with the samples completed first)
     }
     it.L = it.col ? p.H : p.W;
     return it;
@@ -416,8 +418,8 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                 auto prepare = [&](uint32_t c, const Item &it) {
                     const int n = c % NCH, os = c % kNOut;
                     if (it.col) { mbar_arrive(&bars[B_OUT_FULL + os]); return; }
-                    if (p.mode <= MODE_DYNAMIC) { wait_done(p.done + it.b, (unsigned)p.W); fence_proxy_async_all(); }
-                    pdl_wait();                                // (row pass launched ahead of the column pass's completion)
+                    if (p.mode <= MODE_DYNAMIC || p.sync) { wait_done(p.done + it.b, (unsigned)p.W); fence_proxy_async_all(); }
+                    else pdl_wait();                           // (row pass launched ahead of the column pass's completion)
                     uint8_t *dst = smem + S::off_out + os * T::kSlot;
                     mbar_expect_tx(&bars[B_OUT_FULL + os], T::kSlot);
                     if (p.hints) {                                 // the partial is read exactly once
@@ -428,7 +430,9 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                         if constexpr (!BF) tma_load_4d(dst + T::kTile, &mor, &bars[B_OUT_FULL + os], n * kNC + 32, 0, it.i, it.b);
                     }
                 };
-                Item it;
+                Item it, prev;
+                bool has_prev = false;
+                prev.col = prev.b = prev.i = prev.L = 0;
                 for (int k = 0; get_item(k, it); ++k) {
                     const CUtensorMap *mo = it.col ? &moc : &mor;
                     const int cw = it.col ? it.i : 0, ch = it.col ? 0 : it.i;
@@ -453,6 +457,14 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                             if constexpr (!BF) tma_store_4d(mo, slot + T::kTile, n * kNC + 32, cw, ch, it.b);
                         }
                         tma_store_commit();
+                        if (p.sync && n == 0 && has_prev && prev.col) {
+                            // publish the previous column line: its last store was committed a chunk period ago
+                            tma_store_wait_all<1>();
+                            fence_proxy_async_all();
+                            __threadfence();
+                            atomicAdd(p.done + prev.b, 1u);
+                        }
+                        if (n == NCH - 1) { prev = it; has_prev = true; }
                         if (n == NCH - 1) {
                             if (it.col && p.mode <= MODE_DYNAMIC) {
                                 // publish this column line: its stores (async proxy) and the stats written by the softmax group
@@ -477,6 +489,11 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                     }
                 }
                 tma_store_wait_all<0>();
+                if (p.sync && has_prev && prev.col) {         // the last column line of this CTA
+                    fence_proxy_async_all();
+                    __threadfence();
+                    atomicAdd(p.done + prev.b, 1u);
+                }
             }
         }
     } else if (warp >= kWarpConv0) {
@@ -578,8 +595,8 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             CCA_STAMP(3);
             // ---- per-pixel statistics / merge scales (off the MMA's critical path now)
             float sa = 0.f, sb = 0.f;
-            if (!it.col && p.mode <= MODE_DYNAMIC) wait_done(p.done + it.b, (unsigned)p.W);   // column stats of this sample complete
-            if (!it.col) pdl_wait();                           // row pass launched ahead of the column pass's completion
+            if (!it.col && (p.mode <= MODE_DYNAMIC || p.sync)) wait_done(p.done + it.b, (unsigned)p.W);   // column stats of this sample complete
+            else if (!it.col) pdl_wait();                      // row pass launched ahead of the column pass's completion
             if (rvalid) {
                 const long pix = it.col ? ((long)it.b * p.H + r) * p.W + it.i : ((long)it.b * p.H + it.i) * p.W + r;
                 const float mn = m * kLn2;                       // natural-log units
@@ -717,6 +734,7 @@ cudaError_t launch_fwd(const void *q, const void *k, const void *v, void *out, f
     if (keep > d.B) keep = d.B;
     p.hints = tc_l2_hints();
     p.keep_from = mode <= MODE_DYNAMIC ? 0 : d.B - keep;
+    p.sync = (mode == MODE_COL_ONLY || mode == MODE_ROW_ONLY) && tc_pdl() == 2 ? 1 : 0;
     auto kern = cca_tc_fwd_kernel<LK, BF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem<LK, BF>::kBytes);
     if (e != cudaSuccess) return e;
@@ -783,7 +801,10 @@ cudaError_t tc_forward(const void *q, const void *k, const void *v, void *out, f
         if (e != cudaSuccess) return e;
         return go(lkc, fused_mode() == 1 ? MODE_DYNAMIC : MODE_FUSED);
     }
-    cudaError_t e = go(lkc, MODE_COL_ONLY);
+    cudaError_t e = cudaSuccess;
+    if (tc_pdl() == 2) e = cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * (2 * d.B + 2), st);   // done[] of the overlapped row pass
+    if (e != cudaSuccess) return e;
+    e = go(lkc, MODE_COL_ONLY);
     if (e != cudaSuccess) return e;
     return go(lkr, MODE_ROW_ONLY);
 }

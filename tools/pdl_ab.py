@@ -1,4 +1,5 @@
-"""A/B of programmatic dependent launch between the passes of the tcgen05 op (profiling aid)."""
+"""A/B of programmatic dependent launch between the passes of the tcgen05 op: 0 off, 1 dependent launch, 2 dependent launch
+with the second pass overlapping the tail of the first (per-sample completion counters).  Results must be bit-identical."""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -27,10 +28,10 @@ for dt in (torch.float32, torch.bfloat16):
     pdl(0)
     ref_o, ref_l = cca_forward(q, k, v, impl="tc")
     ref_g = cca_backward(do, q, k, v, ref_o, ref_l, impl="tc")
-    for on in (0, 1, 0, 1):
+    for on in (0, 1, 2, 0, 1, 2):
         pdl(on)
         same = True
-        for _ in range(5):
+        for _ in range(5 if on < 2 else 40):
             o, l = cca_forward(q, k, v, impl="tc")
             g = cca_backward(do, q, k, v, o, l, impl="tc")
             same &= bool(torch.equal(o, ref_o) and torch.equal(l, ref_l) and all(torch.equal(a, b) for a, b in zip(g, ref_g)))
