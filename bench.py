@@ -244,10 +244,16 @@ def run_ours(args):
     # current step.  Every step still moves its own x in and its own y, dx out inside the timed region.
     s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     x_dev = [torch.empty(B, C, H, W, device=dev, dtype=dtype) for _ in range(2)]
+    # results are parked in persistent device buffers (one D2D copy each on the compute stream) so that the D2H stream never
+    # holds autograd-owned blocks: no record_stream / caching-allocator interplay, the overlap is deterministic
+    y_dev = [torch.empty(B, C, H, W, device=dev, dtype=dtype) for _ in range(2)]
+    dx_dev = [torch.empty(B, C, H, W, device=dev, dtype=dtype) for _ in range(2)]
     y_hosts = [y_host, torch.empty_like(x_host).pin_memory()]
     dx_hosts = [dx_host, torch.empty_like(x_host).pin_memory()]
-    ev_in = [torch.cuda.Event() for _ in range(2)]
-    ev_free = [torch.cuda.Event() for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]          # x_dev[slot] filled
+    ev_free = [torch.cuda.Event() for _ in range(2)]        # x_dev[slot] consumed by the compute stream
+    ev_res = [torch.cuda.Event() for _ in range(2)]         # y_dev / dx_dev[slot] written by the compute stream
+    ev_out = [torch.cuda.Event() for _ in range(2)]         # y_dev / dx_dev[slot] copied out
     pipe = {"i": 0, "primed": False}
 
     def _prefetch(slot):
@@ -260,7 +266,8 @@ def run_ours(args):
         cur = torch.cuda.current_stream()
         slot = pipe["i"] & 1
         if not pipe["primed"]:
-            ev_free[0].record(cur); ev_free[1].record(cur)
+            for e in ev_free + ev_out:
+                e.record(cur)
             _prefetch(slot)
             pipe["primed"] = True
         _prefetch(slot ^ 1)                                 # next step's input, while this step computes
@@ -269,14 +276,15 @@ def run_ours(args):
         y = net(xd)
         (y * g).sum().backward()
         ev_free[slot].record(cur)
-        done = torch.cuda.Event()
-        done.record(cur)
+        cur.wait_event(ev_out[slot])                        # the D2H of two steps ago has drained these buffers
+        y_dev[slot].copy_(y.detach())
+        dx_dev[slot].copy_(xd.grad)
+        ev_res[slot].record(cur)
         with torch.cuda.stream(s_out):
-            s_out.wait_event(done)
-            y_hosts[slot].copy_(y.detach(), non_blocking=True)
-            dx_hosts[slot].copy_(xd.grad, non_blocking=True)
-        y.record_stream(s_out)
-        xd.grad.record_stream(s_out)
+            s_out.wait_event(ev_res[slot])
+            y_hosts[slot].copy_(y_dev[slot], non_blocking=True)
+            dx_hosts[slot].copy_(dx_dev[slot], non_blocking=True)
+            ev_out[slot].record(s_out)
         net.zero_grad(set_to_none=True)
         pipe["i"] += 1
 
@@ -324,7 +332,7 @@ def run_ours(args):
     module = {"value": px / (ms_mod * 1e-3), "unit": UNIT, "ms_per_step": ms_mod,
               "note": "CrissCrossAttention nn.Module x R fwd+bwd, x resident; includes the stock-torch fp32 1x1 convs"}
     ms_e2e_serial = max_over_ranks(time_events(step_e2e, max(3, args.steps // 2), 3, barrier))
-    ms_e2e = max_over_ranks(time_events(step_e2e_pipelined, max(4, args.steps // 2), 4, barrier, finish=join_streams))
+    ms_e2e = max_over_ranks(time_events(step_e2e_pipelined, max(6, args.steps // 2), 4, barrier, finish=join_streams))
     e2e = {"value": px / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
            "h2d_bytes_per_step": x_host.numel() * esize, "d2h_bytes_per_step": 2 * x_host.numel() * esize,
            "serial_ms_per_step": ms_e2e_serial, "serial_value": px / (ms_e2e_serial * 1e-3),
@@ -363,15 +371,15 @@ def run_ours(args):
     dom_bytes, dom_ms = (bytes_b, b_avg) if dom_is_bwd else (bytes_f, f_avg)
     ach = dom_bytes / (dom_ms * 1e-3) / 1e9
     # DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of one op call from the ncu --set full capture of
-    # tools/run_op.py committed as profiles/r01c_tc_ncu_summary.txt (B=8, C=512, 97x97, fp32, tensor-core kernels)
+    # tools/run_op.py committed as profiles/r01e_tc_ncu_summary.txt (B=8, C=512, 97x97, fp32, tensor-core kernels)
     ncu_traffic = None
     if (B, C, H, W) == (8, 512, 97, 97) and dtype == torch.float32 and op_layout == "channels_last":
-        ncu_traffic = {"fwd": 751.4e6, "bwd": 1579.3e6}
+        ncu_traffic = {"fwd": 745.7e6, "bwd": 1574.4e6}
     roofline = {"bound": "hbm", "kernel": "cca backward op (delta + column pass + row pass)" if dom_is_bwd
                 else "cca forward op (column pass + row pass)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": (ncu_traffic["bwd" if dom_is_bwd else "fwd"] if ncu_traffic else None),
-                "traffic_source": "ncu --set full, profiles/r01c_tc_ncu_summary.txt (sum over the launches of one op call)",
+                "traffic_source": "ncu --set full, profiles/r01e_tc_ncu_summary.txt (sum over the launches of one op call)",
                 "peak_source": peak_src, "launches_per_op": nb if dom_is_bwd else nf,
                 "op_fwd": {"ms": f_avg, "ms_min": f_min, "alg_bytes": bytes_f, "gbs": bytes_f / f_avg / 1e6,
                            "frac": bytes_f / f_avg / 1e6 / peak, "launches": nf},
