@@ -14,16 +14,37 @@ import torch.nn.functional as F
 from .functional import cca, tc_eligible
 
 
-def _project(conv: nn.Conv2d, x_cl: torch.Tensor) -> torch.Tensor:
-    """1x1 conv of a channels-last tensor as one dense GEMM on its [pixels, C] view (cuBLAS via F.linear).
+class _QKVProject(torch.autograd.Function):
+    """The three 1x1 convs of functions.py:29,32,35 on a channels-last tensor, as dense GEMMs on its [pixels, C] view
+    (cuBLAS; same parameters and fp32 maths as ``conv(x)``).  The outputs are channels-last q, k, v -- exactly the layout
+    the tensor-core kernels consume.  One autograd node instead of three so that the input gradient is accumulated inside
+    the GEMMs (beta = 1) rather than by two extra elementwise passes over [pixels, C].  On B200 the GEMM form is ~1.7x
+    faster than the cudnn fp32 1x1 conv (fwd+bwd of the three projections at B=8, C=512, 97x97: 3.9 ms vs 6.7 ms)."""
 
-    Same parameters and fp32 maths as ``conv(x)`` (functions.py:29,32,35); the result is a channels-last tensor, i.e.
-    exactly the layout the tensor-core kernels consume.  On B200 this is ~1.7x faster than the cudnn fp32 1x1 conv
-    (fwd+bwd of the three projections at B=8, C=512, 97x97: 3.9 ms vs 6.7 ms)."""
-    B, C, H, W = x_cl.shape
-    xm = x_cl.permute(0, 2, 3, 1).reshape(B * H * W, C)                    # a view: channels-last memory is [pixels, C]
-    y = F.linear(xm, conv.weight.view(conv.out_channels, C), conv.bias)
-    return y.view(B, H, W, conv.out_channels).permute(0, 3, 1, 2)          # logical NCHW, channels-last strides
+    @staticmethod
+    def forward(ctx, x_cl, wq, bq, wk, bk, wv, bv):
+        B, C, H, W = x_cl.shape
+        xm = x_cl.permute(0, 2, 3, 1).reshape(B * H * W, C)                # a view: channels-last memory is [pixels, C]
+        ws = [w.view(w.shape[0], C) for w in (wq, wk, wv)]
+        outs = [torch.addmm(b, xm, w.t()) for w, b in zip(ws, (bq, bk, bv))]
+        ctx.save_for_backward(xm, *ws)
+        ctx.shape = (B, H, W)
+        ctx.wshapes = (wq.shape, wk.shape, wv.shape)
+        return tuple(y.view(B, H, W, y.shape[1]).permute(0, 3, 1, 2) for y in outs)   # logical NCHW, channels-last strides
+
+    @staticmethod
+    def backward(ctx, dq, dk, dv):
+        xm, wq, wk, wv = ctx.saved_tensors
+        B, H, W = ctx.shape
+        C = xm.shape[1]
+        gs = [g.permute(0, 2, 3, 1).reshape(B * H * W, g.shape[1]) for g in (dq, dk, dv)]   # views of channels-last grads
+        dx = torch.mm(gs[2], wv)
+        dx.addmm_(gs[0], wq)
+        dx.addmm_(gs[1], wk)
+        dws = [torch.mm(g.t(), xm).view(shp) for g, shp in zip(gs, ctx.wshapes)]
+        dbs = [g.sum(0) for g in gs]
+        dx = dx.view(B, H, W, C).permute(0, 3, 1, 2)
+        return dx, dws[0], dbs[0], dws[1], dbs[1], dws[2], dbs[2]
 
 
 class CrissCrossAttention(nn.Module):
@@ -48,9 +69,9 @@ class CrissCrossAttention(nn.Module):
             # tensor-core kernels are channels-last; converting x once (a no-op inside a channels_last network) lets
             # the three 1x1 projections run as plain GEMMs that emit channels-last q/k/v directly
             x = x.contiguous(memory_format=torch.channels_last)
-            q = _project(self.query_conv, x)  # functions.py:29
-            k = _project(self.key_conv, x)    # functions.py:32
-            v = _project(self.value_conv, x)  # functions.py:35
+            q, k, v = _QKVProject.apply(x, self.query_conv.weight, self.query_conv.bias,      # functions.py:29
+                                        self.key_conv.weight, self.key_conv.bias,          # functions.py:32
+                                        self.value_conv.weight, self.value_conv.bias)      # functions.py:35
         else:
             q = self.query_conv(x)            # functions.py:29
             k = self.key_conv(x)              # functions.py:32
@@ -58,7 +79,7 @@ class CrissCrossAttention(nn.Module):
         if q.dtype != v.dtype or k.dtype != v.dtype:       # autocast corner: keep one dtype
             q, k = q.to(v.dtype), k.to(v.dtype)
         o = cca(q, k, v, self.impl)           # functions.py:30-47 fused
-        return self.gamma * o + x             # functions.py:49
+        return torch.addcmul(x, self.gamma, o)          # gamma * o + x in one pass (functions.py:49)
 
 
 class RCCA(nn.Module):
