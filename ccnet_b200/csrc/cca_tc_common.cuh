@@ -24,11 +24,11 @@ constexpr uint32_t kSw128 = 2;   // UMMA smem-descriptor layout type SWIZZLE_128
 constexpr int kThreads = 640;
 constexpr int kConvThreads = 256;
 constexpr int kWarpConv0 = 8, kWarpProducer = 16, kWarpMma = 17, kWarpStore = 18;
-constexpr int kRegsConv = 56, kRegsMisc = 72;   // per kernel: kRegsSoft + kRegsEpi <= 296
+constexpr int kRegsMisc = 72;
 // setmaxnreg moves registers through a per-CTA pool that only holds what the CTA itself released: the increases must be
 // covered by the decreases relative to the launch allocation of 96 regs/thread (640 threads):
-//   released 256*(96-56) + 128*(96-72) = 13312  >=  claimed 128*(168-96) + 128*(128-96) = 13312
-constexpr bool reg_pool_ok(int soft, int epi, int conv = kRegsConv)
+//   released 256*(96-88) + 128*(96-72) = 5120  >=  claimed 128*(104-96) + 128*(128-96) = 5120   (both kernels)
+constexpr bool reg_pool_ok(int soft, int epi, int conv)
 {
     return 256 * (96 - conv) + 128 * (96 - kRegsMisc) >= 128 * (soft - 96) + 128 * (epi - 96);
 }
@@ -86,37 +86,6 @@ __device__ __forceinline__ bool elect_one()
 
 // Converter: one staged slot ([LK px][64 ch] fp32 as two swizzled tiles) -> hi/lo operand planes
 // [8-channel chunk][pixel][16 B].  256 threads: thread t handles pixel (t & 127), octets 4*(t>>7)..+3.
-// bf16 I/O: the slot is one swizzled tile of 64 bf16 channels; the "conversion" is a de-swizzling copy into planes.
-template <int LK, bool BF = false>
-__device__ __forceinline__ void convert_slot(const uint8_t *slot, uint8_t *op, int t)
-{
-    using T = Tiles<LK, BF>;
-    const int r = t & 127, half = t >> 7;
-    if (r >= LK) return;
-    if constexpr (BF) {
-        const uint8_t *src = slot + r * 128;
-        uint8_t *dh = op + r * 16 + half * 4 * T::kPlane;
-        const int sw = r & 7;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4 *>(dh + j * T::kPlane) = *reinterpret_cast<const uint4 *>(src + (((half * 4 + j) ^ sw) * 16));
-        return;
-    }
-    const uint8_t *src = slot + r * 128 + half * T::kTile;      // octets 0-3 live in tile 0, 4-7 in tile 1
-    uint8_t *dh = op + r * 16 + half * 4 * T::kPlane, *dl = dh + 8 * T::kPlane;
-    const int sw = r & 7;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float4 a = *reinterpret_cast<const float4 *>(src + (((2 * j) ^ sw) * 16));
-        const float4 b = *reinterpret_cast<const float4 *>(src + (((2 * j + 1) ^ sw) * 16));
-        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        uint4 hi, lo;
-        split8(v, hi, lo);
-        *reinterpret_cast<uint4 *>(dh + j * T::kPlane) = hi;
-        *reinterpret_cast<uint4 *>(dl + j * T::kPlane) = lo;
-    }
-}
-
 // fp32 tile -> bf16 hi/lo planes IN PLACE (the planes take exactly the bytes of the two fp32 tiles): every converter thread
 // reads and splits its 128 B first, all 256 meet on named barrier 1, then they overwrite the slot.
 template <int LK>
