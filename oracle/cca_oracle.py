@@ -88,6 +88,62 @@ def cca_backward(dout: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.
     return dq, dk, dv
 
 
+def cca_forward_tiled(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, qt: int, kt: int):
+    """The same criss-cross step evaluated the way DESIGN.md 8 plans the next kernel generation: independent
+    (direction, query tile, key block) items.  Phase 1 folds per-item row maxima / sums into the final lse (only q, k);
+    phase 2 lets every item ADD exp(S_item - lse) @ V_item onto a zeroed output -- no partial-output merge chain, any item
+    order, tiles of at most qt queries x kt keys along a line.  Must equal cca_forward (tests/test_oracle.py); it is the
+    restatement the tiled CUDA path will be checked against."""
+    B, _, H, W = q.shape
+    C = v.shape[1]
+    neg = float("-inf")
+    items = []                                            # (direction, line index, query range, key range)
+    for w in range(W):
+        for q0 in range(0, H, qt):
+            for k0 in range(0, H, kt):
+                items.append(("col", w, (q0, min(q0 + qt, H)), (k0, min(k0 + kt, H))))
+    for h in range(H):
+        for q0 in range(0, W, qt):
+            for k0 in range(0, W, kt):
+                items.append(("row", h, (q0, min(q0 + qt, W)), (k0, min(k0 + kt, W))))
+
+    def logits(it):
+        d, i, (a, b), (c, e) = it
+        if d == "col":
+            s = torch.einsum("bcq,bcg->bqg", q[:, :, a:b, i], k[:, :, c:e, i])
+            qi = torch.arange(a, b).view(-1, 1)
+            ki = torch.arange(c, e).view(1, -1)
+            return s.masked_fill((qi == ki).unsqueeze(0), neg)             # the self position of the column branch
+        return torch.einsum("bcq,bcg->bqg", q[:, :, i, a:b], k[:, :, i, c:e])
+
+    # phase 1: running (m, l) per pixel -> lse
+    m = torch.full((B, H, W), neg, dtype=q.dtype)
+    l = torch.zeros((B, H, W), dtype=q.dtype)
+    for it in items:
+        d, i, (a, b), _ = it
+        s = logits(it)
+        mi = s.max(dim=2).values
+        sl = (slice(None), slice(a, b), i) if d == "col" else (slice(None), i, slice(a, b))
+        mo, lo = m[sl], l[sl]
+        mn = torch.maximum(mo, mi)
+        safe = torch.where(torch.isinf(mn), torch.zeros_like(mn), mn)      # an all-masked item (1x1 column tile)
+        l[sl] = lo * torch.exp(mo - safe) + torch.exp(s - safe.unsqueeze(2)).sum(dim=2)
+        m[sl] = mn
+    lse = m + torch.log(l)
+    # phase 2: every item adds its normalised contribution (order-free)
+    out = torch.zeros((B, C, H, W), dtype=v.dtype)
+    for it in reversed(items):                                               # any order
+        d, i, (a, b), (c, e) = it
+        s = logits(it)
+        if d == "col":
+            p = torch.exp(s - lse[:, a:b, i].unsqueeze(2))
+            out[:, :, a:b, i] += torch.einsum("bqg,bcg->bcq", p, v[:, :, c:e, i])
+        else:
+            p = torch.exp(s - lse[:, i, a:b].unsqueeze(2))
+            out[:, :, i, a:b] += torch.einsum("bqg,bcg->bcq", p, v[:, :, i, c:e])
+    return out, lse
+
+
 def cca_forward_bruteforce(q, k, v):
     """Pure-python loops over the criss-cross set of every pixel (tiny inputs only).
 

@@ -93,3 +93,19 @@ def test_softmax_rows_sum_to_one_and_mask_exact_zero():
     assert torch.allclose(a.sum(-1), torch.ones_like(a.sum(-1)))
     idx = torch.arange(6)
     assert (a[0, idx, :, idx] == 0).all()          # masked self entry of the column branch
+
+
+@pytest.mark.parametrize("shape,qt,kt", [((2, 4, 8, 5, 6), 2, 3), ((1, 8, 16, 9, 7), 4, 4), ((1, 2, 4, 1, 5), 1, 2),
+                                         ((1, 2, 4, 6, 1), 3, 1), ((1, 4, 8, 13, 11), 16, 5)])
+def test_tiled_reduce_add_restatement_equals_the_oracle(shape, qt, kt):
+    """The (direction, query tile, key block) decomposition planned for the next kernel generation: final lse
+    first, then order-free normalised contributions added onto a zeroed output.  Exact up to fp64 rounding."""
+    B, Cq, C, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape) + qt + kt)
+    q = torch.randn(B, Cq, H, W, generator=g, dtype=torch.float64)
+    k = torch.randn(B, Cq, H, W, generator=g, dtype=torch.float64)
+    v = torch.randn(B, C, H, W, generator=g, dtype=torch.float64)
+    ro, rl = O.cca_forward(q, k, v)
+    to, tl = O.cca_forward_tiled(q, k, v, qt, kt)
+    assert (to - ro).abs().max().item() <= 1e-12
+    assert (tl - rl).abs().max().item() <= 1e-12
