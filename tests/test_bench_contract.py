@@ -8,7 +8,9 @@ import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LINES = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01e_bench_line*.json")))
+ALL = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01e_bench_line*.json")))
+LINES = [p for p in ALL if "reference_arm" not in p]
+REF_LINES = [p for p in ALL if "reference_arm" in p]
 
 REQUIRED = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
             "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"]
@@ -36,6 +38,20 @@ def test_committed_bench_line_has_the_contract_fields(path):
     if d["n_gpus"] == 1 and d["cpu_baseline"] is not None:
         b = d["cpu_baseline"]
         assert b["kind"] in ("port", "reference") and b["cores"] >= 1 and b["value"] > 0 and b["sample"]
+
+
+@pytest.mark.parametrize("path", REF_LINES, ids=[os.path.basename(p) for p in REF_LINES])
+def test_committed_reference_arm_line(path):
+    """`bench.py --impl reference`: same metric / unit / config as our arm, the CPU reference timed on the host cores."""
+    d = json.load(open(path))
+    ours = json.load(open(LINES[0]))
+    assert d["impl"] == "reference" and d["metric"] == ours["metric"] and d["unit"] == ours["unit"]
+    assert d["higher_is_better"] is True and d["config"]["workload"] == ours["config"]["workload"]
+    b = d["cpu_baseline"]
+    assert b["kind"] in ("port", "reference") and b["cores"] >= 1 and b["sample"] and b["value"] == d["value"]
+    e = d["e2e"]
+    assert e["value"] == d["value"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+    assert d["value"] < 1e-2 * ours["value"]                # the point of the exercise
 
 
 def test_qkv_projection_node_matches_the_three_convs():
