@@ -2,6 +2,7 @@
 // host-buffer variants.  No torch types anywhere in this library.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "cca_common.cuh"
