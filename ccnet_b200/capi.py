@@ -24,7 +24,9 @@ SYMBOLS = {
     "cca_b200_strerror": (ctypes.c_char_p, [_i]),
     "cca_b200_device_ok": (_i, []),
     "cca_b200_launch_count": (ctypes.c_ulonglong, []),
-    "cca_b200_tc_supported": (_i, [_i] * 6),
+    "cca_b200_tc_supported": (_i, [_i] * 7),
+    "cca_b200_item_space": (None, [_i] * 3 + [ctypes.POINTER(_i)]),
+    "cca_b200_decode_item": (None, [_i] * 4 + [ctypes.POINTER(_i)]),
     "cca_b200_workspace_bytes": (_sz, [_i] * 7),
     "cca_b200_forward": (_i, [_vp] * 6 + [_sz] + [_i] * 6 + [_u, _vp]),
     "cca_b200_backward": (_i, [_vp] * 10 + [_sz] + [_i] * 6 + [_u, _vp]),

@@ -6,6 +6,8 @@
 #include <cstring>
 
 #include "cca_common.cuh"
+#include "cca_items.cuh"
+#include "cca_tc_common.cuh"
 
 namespace cca {
 namespace {
@@ -35,30 +37,34 @@ size_t esize(int dtype) { return dtype == CCA_F32 ? 4 : 2; }
 
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
-static int g_l2_hints = -1;
-static double g_l2_keep_mb = 80.0;
-int tc_l2_hints()
+namespace {
+int env_int(const char *name, int dflt, int lo, int hi)
 {
-    if (g_l2_hints < 0) {
-        const char *e = getenv("CCA_B200_L2HINT"), *k = getenv("CCA_B200_L2KEEP_MB");
-        g_l2_hints = e ? (atoi(e) != 0) : 0;      // off by default: no gain measured with two launches per pass
-        if (k && atof(k) >= 0.0) g_l2_keep_mb = atof(k);
-    }
-    return g_l2_hints;
+    const char *e = getenv(name);
+    if (!e) return dflt;
+    const int v = atoi(e);
+    return v < lo || v > hi ? dflt : v;
 }
-double tc_l2_keep_mb() { tc_l2_hints(); return g_l2_keep_mb; }
-void set_tc_l2_hints(int on, double keep_mb) { g_l2_hints = on != 0; g_l2_keep_mb = keep_mb; }
-static int g_pdl = -1;
-int tc_pdl()
+constexpr int kUnset = -1000;
+std::atomic<int> g_pdl{kUnset}, g_zero_ahead{kUnset}, g_delta{kUnset};
+int knob(std::atomic<int> &g, const char *name, int dflt, int lo, int hi)
 {
-    if (g_pdl < 0) {
-        const char *e = getenv("CCA_B200_PDL");
-        g_pdl = e ? atoi(e) : 1;           // 0: off, 1: dependent launch, 2: + overlapped second pass (per-sample counters)
-        if (g_pdl < 0 || g_pdl > 2) g_pdl = 1;
+    int v = g.load(std::memory_order_relaxed);
+    if (v == kUnset) {
+        v = env_int(name, dflt, lo, hi);
+        g.store(v, std::memory_order_relaxed);      // racing first calls compute the same value
     }
-    return g_pdl;
+    return v;
 }
-void set_tc_pdl(int on) { g_pdl = on < 0 || on > 2 ? 1 : on; }
+}  // namespace
+int tc_pdl() { return knob(g_pdl, "CCA_B200_PDL", 1, 0, 1); }
+int tc_zero_ahead() { return knob(g_zero_ahead, "CCA_B200_ZERO_AHEAD", 1, 1, 4); }
+int tc_delta_mode() { return knob(g_delta, "CCA_B200_DELTA", -1, -1, 1); }
+#ifdef CCA_DEBUG_HOOKS
+void set_tc_pdl(int on) { g_pdl.store(on ? 1 : 0); }
+void set_tc_zero_ahead(int n) { g_zero_ahead.store(n < 1 ? 1 : (n > 4 ? 4 : n)); }
+void set_tc_delta_mode(int m) { g_delta.store(m < -1 || m > 1 ? -1 : m); }
+#endif
 }  // namespace cca
 
 using namespace cca;
@@ -66,14 +72,14 @@ using namespace cca;
 extern "C" {
 
 int cca_b200_version(void) { return CCA_B200_VERSION; }
-// profiling aid (not declared in the public header): device buffer of 2 x 4 x 512 int64 clock stamps
+#ifdef CCA_DEBUG_HOOKS
+// A/B and profiling aids of debug builds (`python -m ccnet_b200.build --debug`); not part of the ABI, absent from release builds
 CCA_API void cca_b200__set_debug_buffer(void *p) { set_tc_debug_buffer(p); }
-// A/B aid: run the tensor-core forward as two launches (column pass, row pass) instead of the fused launch
-CCA_API void cca_b200__set_two_pass(int on) { set_tc_two_pass(on); }
 CCA_API void cca_b200__set_bwd_debug_buffer(void *p) { set_tc_bwd_debug_buffer(p); }
-// A/B aid: L2 eviction hints on / off and the evict_last budget in MB
-CCA_API void cca_b200__set_l2_hints(int on, double keep_mb) { set_tc_l2_hints(on, keep_mb); }
 CCA_API void cca_b200__set_pdl(int on) { set_tc_pdl(on); }
+CCA_API void cca_b200__set_zero_ahead(int n) { set_tc_zero_ahead(n); }
+CCA_API void cca_b200__set_delta_mode(int m) { set_tc_delta_mode(m); }
+#endif
 const char *cca_b200_last_error(void) { return g_err; }
 const char *cca_b200_strerror(int s)
 {
@@ -89,6 +95,32 @@ const char *cca_b200_strerror(int s)
 }
 unsigned long long cca_b200_launch_count(void) { return g_launches.load(); }
 
+namespace {
+// compute capability major of the current device, cached per device id (0 on failure)
+int device_major()
+{
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (dev < 0 || dev >= 64) dev = 0;
+    int v = cache[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+        v = major;
+        cache[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+int check_device()
+{
+    const int major = device_major();
+    if (major == 0) return fail(CCA_ERR_CUDA, "cannot query the current CUDA device%s%s");
+    if (major != 10) return fail(CCA_ERR_DEVICE, "the current device is not sm_100 (B200); this library has no other code path%s%s");
+    return CCA_OK;
+}
+}  // namespace
+
 int cca_b200_device_ok(void)
 {
     int dev = 0, major = 0;
@@ -99,20 +131,40 @@ int cca_b200_device_ok(void)
     return major == 10 ? 1 : 0;
 }
 
-int cca_b200_tc_supported(int B, int Cq, int C, int H, int W, int dtype)
+int cca_b200_tc_supported(int which, int B, int Cq, int C, int H, int W, int dtype)
 {
     if (check_dims(B, Cq, C, H, W, dtype)) return 0;
-    return tc_forward_supported(Dims{B, Cq, C, H, W}, dtype) ? 1 : 0;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0 && device_major() != 10) return 0;   // (no device at all: shape answer only)
+    const Dims d{B, Cq, C, H, W};
+    return (which == CCA_WS_BACKWARD ? tc_backward_supported(d, dtype) : tc_forward_supported(d, dtype)) ? 1 : 0;
 }
 
 size_t cca_b200_workspace_bytes(int which, int B, int Cq, int C, int H, int W, int dtype)
 {
-    (void)Cq; (void)C; (void)dtype;
+    (void)dtype;
+    if (B <= 0 || Cq <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+    const Dims d{B, Cq, C, H, W};
     const size_t pix = (size_t)B * H * W;
-    // forward: per-pixel (m,l) of the column pass + per-sample completion counters of the fused launch;
-    // backward: per-pixel delta = <dout, out> + the same counters
-    const size_t counters = (((size_t)(2 * B + 2) * sizeof(unsigned int)) + 15) & ~(size_t)15;   // queue heads + per-sample counters
-    return (which == CCA_WS_FORWARD ? pix * sizeof(float2) : pix * sizeof(float)) + counters;
+    // generic kernels: per-pixel (m,l) of the column pass (forward) / delta (backward); tensor-core kernels: partial lse
+    // planes + zero-ahead counters (forward) / delta + counters (backward).  One size that covers whichever family runs.
+    const size_t simt = (which == CCA_WS_FORWARD ? pix * sizeof(float2) : pix * sizeof(float)) + 16;
+    const size_t tcb = which == CCA_WS_FORWARD ? tc_forward_workspace(d) : tc_backward_workspace(d);
+    return simt > tcb ? simt : tcb;
+}
+
+void cca_b200_item_space(int B, int H, int W, int *out8)
+{
+    const tc::ItemSpace s = tc::make_space(B, H, W);
+    out8[0] = s.total; out8[1] = s.per_sample; out8[2] = s.seg0; out8[3] = s.seg1; out8[4] = s.seg2;
+    out8[5] = s.col.nt; out8[6] = s.row.nt; out8[7] = tc::lk_for(tc::max_tile(s));
+}
+void cca_b200_decode_item(int B, int H, int W, int index, int *out10)
+{
+    const tc::ItemSpace s = tc::make_space(B, H, W);
+    const tc::Item it = tc::decode_item(s, index);
+    out10[0] = it.col; out10[1] = it.b; out10[2] = it.line; out10[3] = it.iq; out10[4] = it.ik;
+    out10[5] = it.q0; out10[6] = it.lq; out10[7] = it.k0; out10[8] = it.lk; out10[9] = it.j;
 }
 
 int cca_b200_forward(const void *q, const void *k, const void *v, void *out, float *lse, void *ws, size_t ws_bytes,
@@ -125,6 +177,7 @@ int cca_b200_forward(const void *q, const void *k, const void *v, void *out, flo
         return fail(CCA_ERR_WORKSPACE, "forward workspace too small%s%s");
     if ((flags & CCA_FLAG_FORCE_SIMT) && (flags & CCA_FLAG_FORCE_TC))
         return fail(CCA_ERR_INVALID, "FORCE_SIMT and FORCE_TC are exclusive%s%s");
+    if ((rc = check_device())) return rc;
     const Dims d{B, Cq, C, H, W};
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const char *why = "";
@@ -159,6 +212,9 @@ int cca_b200_backward(const void *dout, const void *q, const void *k, const void
         return fail(CCA_ERR_INVALID, "null pointer%s%s");
     if (ws_bytes < cca_b200_workspace_bytes(CCA_WS_BACKWARD, B, Cq, C, H, W, dtype))
         return fail(CCA_ERR_WORKSPACE, "backward workspace too small%s%s");
+    if ((flags & CCA_FLAG_FORCE_SIMT) && (flags & CCA_FLAG_FORCE_TC))
+        return fail(CCA_ERR_INVALID, "FORCE_SIMT and FORCE_TC are exclusive%s%s");
+    if ((rc = check_device())) return rc;
     const Dims d{B, Cq, C, H, W};
     const char *why = "";
     const bool nhwc = (flags & CCA_FLAG_NHWC) != 0;

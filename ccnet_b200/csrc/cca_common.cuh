@@ -40,23 +40,32 @@ cudaError_t simt_backward(const void *dout, const void *q, const void *k, const 
 bool simt_supported(Dims d, bool backward);
 
 bool tc_forward_supported(Dims d, int dtype);
+size_t tc_forward_workspace(Dims d);
 cudaError_t tc_forward(const void *q, const void *k, const void *v, void *out, float *lse, void *ws,
                        Dims d, int dtype, cudaStream_t st, const char **why);
+// statistics pre-pass of the tensor-core forward (cca_tc_stats.cu): partial lse planes; also clears a byte range and counters
+cudaError_t tc_stats(const void *q, const void *k, float *parts, void *zero_ptr, long zero_bytes, unsigned int *counters,
+                     int n_counters, Dims d, int dtype, cudaStream_t st, const char **why);
 
 bool tc_backward_supported(Dims d, int dtype);
+size_t tc_backward_workspace(Dims d);
 cudaError_t tc_backward(const void *dout, const void *q, const void *k, const void *v, const void *out, const float *lse,
                         void *dq, void *dk, void *dv, void *ws, Dims d, int dtype, cudaStream_t st, const char **why);
 
 void count_launch(int n = 1);
-void set_tc_debug_buffer(void *p);
-void set_tc_two_pass(int on);
-void set_tc_bwd_debug_buffer(void *p);
-// L2 eviction hints of the tensor-core kernels (CCA_B200_L2HINT = 0/1, CCA_B200_L2KEEP_MB = budget of evict_last data)
-int tc_l2_hints();
-double tc_l2_keep_mb();
-void set_tc_l2_hints(int on, double keep_mb);
-// programmatic dependent launch between the passes of one op (CCA_B200_PDL = 0/1, default 1)
+// Launch knobs of the tensor-core kernels, read once from the environment (std::atomic, safe under DataParallel threads):
+//   CCA_B200_PDL = 0/1        programmatic dependent launch between the launches of one op (default 1)
+//   CCA_B200_ZERO_AHEAD = n   the items of sample b clear the outputs of sample b+n (default 1)
+//   CCA_B200_DELTA = -1/0/1   backward: -1 automatic, 0 every item computes delta, 1 column items produce it for the sample
 int tc_pdl();
+int tc_zero_ahead();
+int tc_delta_mode();
+#ifdef CCA_DEBUG_HOOKS
 void set_tc_pdl(int on);
+void set_tc_zero_ahead(int n);
+void set_tc_delta_mode(int m);
+void set_tc_debug_buffer(void *p);
+void set_tc_bwd_debug_buffer(void *p);
+#endif
 
 }  // namespace cca

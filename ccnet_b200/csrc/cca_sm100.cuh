@@ -34,13 +34,47 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// Bounded spin: a broken pipeline traps instead of hanging the GPU (see gpurun strike rule).
+// Debug builds (-DCCA_SPIN_TRAP=1, `python -m ccnet_b200.build --debug`): a broken pipeline traps after a bounded spin
+// instead of hanging the GPU.  Release builds wait without a bound (a trap would take the whole CUDA context of a
+// training job with it).
+#ifndef CCA_SPIN_TRAP
+#define CCA_SPIN_TRAP 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
+#if CCA_SPIN_TRAP
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 26)) { __trap(); }
     }
+#else
+    while (!mbar_try_wait(bar, parity)) {}
+#endif
+}
+// Spin until a global counter (bumped with a release by other CTAs) reaches `need`.
+__device__ __forceinline__ void wait_count(const unsigned int *cnt, unsigned int need)
+{
+    unsigned int v;
+#if CCA_SPIN_TRAP
+    unsigned int spins = 0;
+#endif
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+        if (v >= need) return;
+        __nanosleep(64);
+#if CCA_SPIN_TRAP
+        if (++spins > (1u << 24)) __trap();
+#endif
+    }
+}
+// all-state-space proxy fence: orders generic-proxy accesses (atomics, ld/st) against async-proxy ones (TMA) of this thread
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// publish: everything this thread's TMA stores / reduce-adds wrote (all groups complete) happens-before the counter bump
+__device__ __forceinline__ void publish_count(unsigned int *cnt)
+{
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __threadfence();
+    atomicAdd(cnt, 1u);
 }
 
 // ---------------------------------------------------------------- programmatic dependent launch
@@ -119,6 +153,12 @@ __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap *m, const vo
         "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;"
         ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
         : "memory");
+}
+// plain (non-tensor) bulk copy shared -> global; 16-byte aligned addresses, size a multiple of 16
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(reinterpret_cast<uint64_t>(gdst)), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read()

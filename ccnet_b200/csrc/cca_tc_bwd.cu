@@ -1,22 +1,30 @@
 // tcgen05 / TMA backward kernel of criss-cross attention for sm_100a (channels-last tensors).
 //
-// Closed form of SURVEY.md 8(a) row a11 (autograd of cc_attention/functions.py:38-47), flash-style: the
-// attention matrix is recomputed per line from (q, k, lse), never stored.  As in the forward, a row and a
-// column of a channels-last image are the same object, so one kernel runs twice:
-//   pass 1 (columns, self entry masked): dq, dk, dv  = column-branch contributions
-//   pass 2 (rows)                      : dq, dk, dv += row-branch contributions (TMA reduce-add, performed at L2)
-// Each line CTA owns all outputs of its line: no atomics, deterministic.
-//
-// Per line (jq = query pixel, jk = key pixel, both < L <= LK):
+// Closed form of SURVEY.md 8(a) row a11 (autograd of cc_attention/functions.py:38-47), flash-style: the attention matrix is
+// recomputed per item from (q, k, lse), never stored.  Items are those of cca_items.cuh (direction, sample, line, query
+// tile, key block); because P = exp(S - lse) uses the FINAL lse, every item is independent and ADDS its contributions:
 //   S  = Q K^T                     (K-dim Cq)        P  = exp(S - lse[jq])            [TMEM -> planes in smem]
 //   dP = dO V^T                    (K-dim C, chunked, accumulated in TMEM over the V/dO chunks)
-//   dV[jk,c] = sum_jq P[jq,jk] dO[jq,c]   per chunk   (A = P planes read MN-major = P^T, B = dO chunk)
+//   dV[jk,c] += sum_jq P[jq,jk] dO[jq,c]   per chunk  (A = P planes read MN-major = P^T, B = dO chunk)
 //   dS = P * (dP - delta[jq])      [planes overwrite P]
-//   dQ[jq,c] = sum_jk dS[jq,jk] K[jk,c]   (A = dS planes K-major)     dK[jk,c] = sum_jq dS[jq,jk] Q[jq,c]  (A = dS^T)
-// All GEMMs run as bf16x3 split MMAs (hi*hi + hi*lo + lo*hi) with fp32 accumulation in TMEM.
-// The same operand planes serve several GEMMs: planes over channels are a K-major operand when the
-// contraction runs over channels (S, dP) and an MN-major B operand when channels are the output (dV, dQ, dK);
-// planes over key pixels are K-major A for dQ and MN-major A (= transpose) for dV / dK.
+//   dQ[jq,c] += sum_jk dS[jq,jk] K[jk,c]   (A = dS planes K-major)     dK[jk,c] += sum_jq dS[jq,jk] Q[jq,c]  (A = dS^T)
+// ONE persistent launch walks the items sample by sample (column items, then row items of the same sample): the second
+// direction finds q,k,v,dO in L2 and its TMA reduce-adds land on dq/dk/dv lines that are still L2-resident.
+//
+// delta[jq] = sum_c dO[jq,c] O[jq,c] is folded into the items (no separate pass over dO and O): the O chunk of the query
+// pixels rides the same ring as V and dO, and the converter warps -- which touch every dO element anyway -- accumulate the
+// dot products.  Two modes: every item computes delta for itself (no dependency), or only the column items of the first key
+// block do, publish it through global memory and a per-sample counter, and the other items of the sample wait for that counter
+// right before their dS phase (such items always have a higher index than the producers: no cyclic waits).
+//
+// Zero-ahead (dq, dk, dv need no initialisation by the caller): as in the forward (cca_tc_fwd.cu), the items of sample b
+// clear 1/per_sample of sample b+ahead's slices, a prep kernel clears the first `ahead` samples and the counters.
+//
+// All GEMMs run as bf16x3 split MMAs (hi*hi + hi*lo + lo*hi) with fp32 accumulation in TMEM (single bf16 MMAs for bf16 I/O).
+// The same operand planes serve several GEMMs: planes over channels are a K-major operand when the contraction runs over
+// channels (S, dP) and an MN-major B operand when channels are the output (dV, dQ, dK); planes over key pixels are K-major A
+// for dQ and MN-major A (= transpose) for dV / dK.
+#include "cca_items.cuh"
 #include "cca_tc_common.cuh"
 
 namespace cca {
@@ -25,40 +33,34 @@ using namespace tc;
 
 constexpr int kTmemCols = 512;      // S / dP double buffer: [0,128) [128,256)   O0: [256,320)   O1: [320,384)
 constexpr int kTmemO = 256;
-// converters keep a whole 128 B row live across the barrier of the in-place conversion (88 registers); the P/dS group streams
-// its rows from TMEM 16 columns at a time
 constexpr int kRegsSoft = 104, kRegsEpi = 128, kRegsConvB = 88;
 static_assert(reg_pool_ok(kRegsSoft, kRegsEpi, kRegsConvB), "setmaxnreg pool");
+constexpr int kZeroBuf = 2048;
 
 struct BwdParams {
-    int B, H, W, C, Cq;
-    int L, NL, col;
-    int sync;              // 1: the row pass runs overlapped with the tail of the column pass (programmatic dependent launch);
-    unsigned int *done;    // done[b] counts the column lines of sample b whose dq/dk/dv stores are complete, and a row line
-                           // only waits for the column lines of its own sample before it accumulates onto them
-    int hints, keep_from;  // L2 eviction hints: the column pass keeps (evict_last) the lines of samples >= keep_from for the row
-                           // pass, which walks the samples backwards; everything else streams (evict_first)
+    ItemSpace sp;
+    int C, Cq;
+    long npix;
     const float *lse;
-    const float *delta;
+    float *delta;              // [B,H,W] (delta_mode 1 only)
+    unsigned int *zdone;       // [B] zero shares of sample b completed
+    unsigned int *ddone;       // [B] delta producers of sample b done (delta_mode 1)
+    int delta_mode;            // 0: every item computes its own delta; 1: column / first-key-block items produce, the rest wait
+    uint8_t *dq, *dk, *dv;
+    long sb_q, sb_v;           // bytes per sample of dq (= dk) and dv
+    long share_q, share_v;     // zero share per item
+    int ahead;
     long long *dbg;
 };
 
+#ifdef CCA_TIMELINE
 #define CCA_STAMP(role)                                                                          \
     do {                                                                                         \
         if (p.dbg && blockIdx.x == 0 && dbg_n < 512) p.dbg[(role) * 512 + dbg_n++] = clock64();  \
     } while (0)
-
-__device__ __forceinline__ void wait_count(const unsigned int *cnt, unsigned int need)
-{
-    unsigned int spins = 0, v;
-    for (;;) {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
-        if (v >= need) return;
-        __nanosleep(64);
-        if (++spins > (1u << 24)) __trap();      // a broken dependency chain traps instead of hanging the GPU
-    }
-}
-__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async;" ::: "memory"); }
+#else
+#define CCA_STAMP(role) do { } while (0)
+#endif
 
 template <int LK, bool BF> struct BwdSmem {
     using T = Tiles<LK, BF>;
@@ -68,25 +70,86 @@ template <int LK, bool BF> struct BwdSmem {
     static constexpr int off_out = off_ld + kNLd * T::kSlot; // 1 out slot (the epilogue has slack; the store warp drives it)
     static constexpr int off_p = off_out + T::kSlot;       // P / dS planes (hi, lo); M=128 over-reads of a slot land in the next slot / here
     static constexpr int off_tail = off_p + T::kP + (16 - LK / 8) * T::kPlane;   // pad for the P^T over-read (16 planes of 8 key pixels)
-    static constexpr int off_bar = off_tail + (128 - LK) * 16 + 256;
-    static constexpr int kBytes = off_bar + 320;
+    static constexpr int off_zero = off_tail + (128 - LK) * 16 + 256;            // zero tile of the zero-ahead copies
+    static constexpr int off_dpart = off_zero + kZeroBuf;  // float [2][128]: per-pixel delta halves from the converters
+    static constexpr int off_bar = off_dpart + 1024;
+    static constexpr int kBytes = off_bar + 8 * 40 + 32;
     static_assert(kBytes <= 232448, "shared memory budget");
 };
 
 enum { B_LD_FULL = 0, B_LD_EMPTY = 6, B_OP_FULL = 12, B_S_FULL = 18, B_S_EMPTY = 20, B_P_FULL = 22,
        B_P_EMPTY = 23, B_O_FULL = 24, B_O_EMPTY = 26, B_OUT_FULL = 28, B_STAGED = 29, B_DP_FULL = 30, B_DS_FULL = 31,
-       B_COUNT = 32 };
+       B_DELTA_FULL = 32, B_DELTA_EMPTY = 33, B_COUNT = 34 };
 
-// Per line the ring carries  Q K (V_n dO_n)* Q K ; item g lives in load slot g % kNLd (fp32: converted in place), so the
-// loads and conversions of the next chunks overlap the MMAs of the current one.  MMAs per line: S (phase A), per chunk dP += dO V^T then
-// dV = P^T dO (phase B; the V buffer is released right after the dP MMAs), dS by the P/dS group (phase C),
-// dQ = dS K and dK = dS^T Q (phase D).
+// does this item compute delta itself (its ring carries the O chunks)?
+__device__ __forceinline__ bool calc_delta(const BwdParams &p, const Item &it) { return p.delta_mode == 0 || (it.col && it.ik == 0); }
+
+// Converter step for a (dO, O) pair of ring slots: returns this thread's part of sum_c dO[r][c] * O[r][c] over its 32 channels of
+// the chunk and (fp32) rewrites the dO slot in place as bf16 hi/lo planes.  All 256 converter threads; thread 0 releases the O slot.
+template <int LK, bool BF>
+__device__ __forceinline__ float convert_dot(uint8_t *dslot, const uint8_t *oslot, int t, uint64_t *o_empty)
+{
+    using T = Tiles<LK, BF>;
+    const int r = t & 127, half = t >> 7;
+    const int rr = r < LK ? r : LK - 1;
+    const int sw = rr & 7;
+    float acc = 0.f;
+    if constexpr (BF) {
+        const uint8_t *a = dslot + rr * 128, *b = oslot + rr * 128;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int j = half * 4 + i;
+            const uint4 x = *reinterpret_cast<const uint4 *>(a + ((j ^ sw) * 16));
+            const uint4 y = *reinterpret_cast<const uint4 *>(b + ((j ^ sw) * 16));
+            const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc += bf_lo(xw[e]) * bf_lo(yw[e]) + bf_hi(xw[e]) * bf_hi(yw[e]);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kConvThreads) : "memory");
+        if (t == 0) mbar_arrive(o_empty);
+    } else {
+        float4 raw[8];
+        const uint8_t *src = dslot + rr * 128 + half * T::kTile;
+        const uint8_t *osrc = oslot + rr * 128 + half * T::kTile;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) raw[j] = *reinterpret_cast<const float4 *>(src + ((j ^ sw) * 16));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 o = *reinterpret_cast<const float4 *>(osrc + ((j ^ sw) * 16));
+            acc += raw[j].x * o.x + raw[j].y * o.y + raw[j].z * o.z + raw[j].w * o.w;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kConvThreads) : "memory");
+        if (t == 0) mbar_arrive(o_empty);
+        if (r < LK) {
+            uint8_t *dh = dslot + r * 16 + half * 4 * T::kPlane, *dl = dh + 8 * T::kPlane;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 a = raw[2 * j], b = raw[2 * j + 1];
+                const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                uint4 hi, lo;
+                split8(v, hi, lo);
+                *reinterpret_cast<uint4 *>(dh + j * T::kPlane) = hi;
+                *reinterpret_cast<uint4 *>(dl + j * T::kPlane) = lo;
+            }
+        }
+    }
+    return acc;
+}
+
+// Per item the ring carries  Q K | (V_n dO_n [O_n])* | Q' K' (next item) | Q K (again, for dQ / dK); item g lives in load slot
+// g % kNLd (fp32: converted in place), so the loads and conversions of the next chunks overlap the MMAs of the current one.
+// MMAs per item: S (phase A), per chunk dP += dO V^T then dV = P^T dO (phase B; the V buffer is released right after the dP
+// MMAs), dS by the P/dS group (phase C), dQ = dS K and dK = dS^T Q (phase D).
 template <int LK, bool BF>
 __global__ void __launch_bounds__(kThreads, 1)
-cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
-                  const __grid_constant__ CUtensorMap mv, const __grid_constant__ CUtensorMap mdo,
-                  const __grid_constant__ CUtensorMap mdq, const __grid_constant__ CUtensorMap mdk,
-                  const __grid_constant__ CUtensorMap mdv, BwdParams p)
+cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant__ CUtensorMap mqr,
+                  const __grid_constant__ CUtensorMap mkc, const __grid_constant__ CUtensorMap mkr,
+                  const __grid_constant__ CUtensorMap mvc, const __grid_constant__ CUtensorMap mvr,
+                  const __grid_constant__ CUtensorMap mdoc, const __grid_constant__ CUtensorMap mdor,
+                  const __grid_constant__ CUtensorMap moc, const __grid_constant__ CUtensorMap mor,
+                  const __grid_constant__ CUtensorMap mdqc, const __grid_constant__ CUtensorMap mdqr,
+                  const __grid_constant__ CUtensorMap mdkc, const __grid_constant__ CUtensorMap mdkr,
+                  const __grid_constant__ CUtensorMap mdvc, const __grid_constant__ CUtensorMap mdvr, BwdParams p)
 {
     using T = Tiles<LK, BF>;
     using S = BwdSmem<LK, BF>;
@@ -95,13 +158,13 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S::off_bar);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::off_bar + 8 * B_COUNT);
+    float *dpart = reinterpret_cast<float *>(smem + S::off_dpart);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NCH = p.C / kNC;
     const int KQ = p.Cq / 16;
-    const int NI = 4 + 2 * NCH;               // load items per line: Q K (V dO)* Q K
-    const int NO = NCH + 2;                   // output items per line: dV chunks, dQ, dK
-    const int total_lines = p.B * p.NL;
-    const int nk = (total_lines - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int NO = NCH + 2;                   // output tiles per item: dV chunks, dQ, dK
+    const int nk = p.sp.total > (int)blockIdx.x ? (p.sp.total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    auto item_of = [&](int k) { return decode_item(p.sp, (int)blockIdx.x + k * (int)gridDim.x); };
 
     if (tid == 0) {
         for (int i = 0; i < kNLd; ++i) {
@@ -112,32 +175,21 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
         for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_S_FULL + i], 1); mbar_init(&bars[B_S_EMPTY + i], 128); }
         mbar_init(&bars[B_P_FULL], 128); mbar_init(&bars[B_P_EMPTY], 1);
         mbar_init(&bars[B_DP_FULL], 1);  mbar_init(&bars[B_DS_FULL], 128);
+        mbar_init(&bars[B_DELTA_FULL], kConvThreads); mbar_init(&bars[B_DELTA_EMPTY], 128);
         fence_mbar_init();
-        prefetch_tmap(&mq); prefetch_tmap(&mk); prefetch_tmap(&mv); prefetch_tmap(&mdo);
-        prefetch_tmap(&mdq); prefetch_tmap(&mdk); prefetch_tmap(&mdv);
+        prefetch_tmap(&mqc); prefetch_tmap(&mqr); prefetch_tmap(&mkc); prefetch_tmap(&mkr); prefetch_tmap(&mvc); prefetch_tmap(&mvr);
+        prefetch_tmap(&mdoc); prefetch_tmap(&mdor); prefetch_tmap(&moc); prefetch_tmap(&mor);
+        prefetch_tmap(&mdqc); prefetch_tmap(&mdqr); prefetch_tmap(&mdkc); prefetch_tmap(&mdkr); prefetch_tmap(&mdvc); prefetch_tmap(&mdvr);
+    }
+    if (tid < kZeroBuf / 16) {                                 // zero tile (read by the async proxy: fence before the barrier)
+        reinterpret_cast<uint4 *>(smem + S::off_zero)[tid] = make_uint4(0, 0, 0, 0);
+        fence_proxy_async();
     }
     if (warp == 0) tmem_alloc<kTmemCols>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    // Programmatic dependent launch: the column pass is launched behind the delta kernel and the row pass behind the column
-    // pass, each without waiting for its predecessor to finish.  Only two places touch what the predecessor produces: the
-    // P/dS group reads delta (column pass <- delta kernel), the store warp accumulates onto dq/dk/dv (row pass <- column pass).
-    pdl_launch_dependents();
-
-    auto line_of = [&](int k) { return (int)blockIdx.x + k * (int)gridDim.x; };
-    auto line_coords = [&](int line, int &cw, int &ch, int &cb) {
-        cb = line / p.NL;
-        const int i = line - cb * p.NL;
-        // second pass: samples backwards (the tail of the column pass is still in L2) -- unless it overlaps the column pass,
-        // whose first samples are complete first
-        if (!p.col && !p.sync) cb = p.B - 1 - cb;
-        if (p.col) { cw = i; ch = 0; } else { cw = 0; ch = i; }
-    };
-    // output item i of a line: i < NCH -> dV chunk i; NCH -> dQ; NCH+1 -> dK
-    auto out_map = [&](int i) -> const CUtensorMap * { return i < NCH ? &mdv : (i == NCH ? &mdq : &mdk); };
-    auto out_c0 = [&](int i) { return i < NCH ? i * kNC : 0; };
 
     if (warp >= kWarpProducer) {
         reg_dec<kRegsMisc>();
@@ -146,30 +198,41 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
             if (lane == 0) {
                 uint32_t g = 0;
                 int dbg_n = 0;
-                const uint64_t pol_keep = p.hints ? l2_policy_evict_last() : l2_policy_evict_normal();
-                const uint64_t pol_stream = p.hints ? l2_policy_evict_first() : l2_policy_evict_normal();
-                auto emit = [&](const CUtensorMap *m, int c0, int line) {
-                    int cw, ch, cb;
-                    line_coords(line, cw, ch, cb);
-                    const uint64_t pol = p.col && cb >= p.keep_from ? pol_keep : pol_stream;
+                (void)dbg_n;
+                auto emit = [&](const CUtensorMap *mc, const CUtensorMap *mr, int c0, const Item &it, int start) {
+                    const CUtensorMap *m = it.col ? mc : mr;
+                    const int cw = it.col ? it.line : start, ch = it.col ? start : it.line;
                     const int slot = g % kNLd;
                     mbar_wait(&bars[B_LD_EMPTY + slot], ((g / kNLd) & 1) ^ 1);
                     CCA_STAMP(0);
                     uint8_t *dst = smem + S::off_ld + slot * T::kSlot;
                     mbar_expect_tx(&bars[B_LD_FULL + slot], T::kSlot);
-                    tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, cb, pol);
-                    if constexpr (!BF) tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, cb, pol);
+                    tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, it.b);
+                    if constexpr (!BF) tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, it.b);
                     ++g;
                 };
-                // ring:  Q0 K0 | (V dO)* Q1 K1 Q0 K0 | (V dO)* Q2 K2 Q1 K1 | ...   (S of the next line is issued while the
-                // dS of the current one is being computed; Q,K of the current line come back for dQ/dK)
-                emit(&mq, 0, line_of(0));
-                emit(&mk, 0, line_of(0));
+                // ring:  Q0 K0 | (V dO [O])* Q1 K1 Q0 K0 | (V dO [O])* Q2 K2 Q1 K1 | ...   (S of the next item is issued while the
+                // dS of the current one is being computed; Q,K of the current item come back for dQ/dK)
+                if (nk > 0) {
+                    const Item it0 = item_of(0);
+                    emit(&mqc, &mqr, 0, it0, it0.q0);
+                    emit(&mkc, &mkr, 0, it0, it0.k0);
+                }
                 for (int k = 0; k < nk; ++k) {
-                    for (int n = 0; n < NCH; ++n) { emit(&mv, n * kNC, line_of(k)); emit(&mdo, n * kNC, line_of(k)); }
-                    if (k + 1 < nk) { emit(&mq, 0, line_of(k + 1)); emit(&mk, 0, line_of(k + 1)); }
-                    emit(&mq, 0, line_of(k));
-                    emit(&mk, 0, line_of(k));
+                    const Item it = item_of(k);
+                    const bool calc = calc_delta(p, it);
+                    for (int n = 0; n < NCH; ++n) {
+                        emit(&mvc, &mvr, n * kNC, it, it.k0);
+                        emit(&mdoc, &mdor, n * kNC, it, it.q0);
+                        if (calc) emit(&moc, &mor, n * kNC, it, it.q0);
+                    }
+                    if (k + 1 < nk) {
+                        const Item nx = item_of(k + 1);
+                        emit(&mqc, &mqr, 0, nx, nx.q0);
+                        emit(&mkc, &mkr, 0, nx, nx.k0);
+                    }
+                    emit(&mqc, &mqr, 0, it, it.q0);
+                    emit(&mkc, &mkr, 0, it, it.k0);
                 }
             }
         } else if (warp == kWarpMma) {
@@ -181,12 +244,13 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
             const uint32_t LO8 = 8 * T::kPlane, LOP = T::kPP * T::kPlane;
             uint32_t u = 0, oc = 0;
             int dbg_n = lane == 0 ? 0 : 512;
+            (void)dbg_n;
             // operand of ring item g = load slot g % kNLd: fp32 -> bf16 hi/lo planes written in place (K-major / MN-major by descriptor);
             //                  bf16 -> the TMA tile itself read with SWIZZLE_128B descriptors:
             //                          K-major use: k-step = +32 B; MN-major use: k-step = +2048 B (16 pixel rows)
             const uint32_t ld_base = smem_u32(smem + S::off_ld);
             auto opb = [&](uint32_t g) { return ld_base + (g % kNLd) * T::kSlot; };
-            auto wait_op = [&](uint32_t g) { mbar_wait(&bars[(BF ? B_LD_FULL : B_OP_FULL) + g % kNLd], (g / kNLd) & 1); };
+            auto wait_op = [&](uint32_t g) { mbar_wait(&bars[B_OP_FULL + g % kNLd], (g / kNLd) & 1); };
             auto free_op = [&](uint32_t g) { commit_to(&bars[B_LD_EMPTY + g % kNLd]); };
             // channel-tile operand parameters: (k-step, lbo, sbo, layout) when the contraction runs over channels (kmaj) or
             // over pixels (mnmaj)
@@ -208,16 +272,17 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                 free_op(u); free_op(u + 1);
                 u += 2;
             };
-            issue_s(0);
+            if (nk > 0) issue_s(0);
             for (int k = 0; k < nk; ++k) {
+                const bool calc = calc_delta(p, item_of(k));
                 CCA_STAMP(2);
                 const uint32_t sdp = tmem + (k & 1) * 128;        // S(k), then dP(k)
                 mbar_wait(&bars[B_P_FULL], k & 1);
                 CCA_STAMP(2);
                 // ---- phase B: per chunk  dP += dO V^T  and  dV = P^T dO
-                for (int n = 0; n < NCH; ++n, u += 2, ++oc) {
+                for (int n = 0; n < NCH; ++n, u += calc ? 3 : 2, ++oc) {
                     const uint32_t vb = opb(u), db = opb(u + 1);
-                    wait_op(u); wait_op(u + 1);
+                    wait_op(u); wait_op(u + 1);                   // (calc: the converters have also read dO for delta)
                     tc_fence_after();
                     mma_split3_loop<kNC / 16, TERMS>(sdp, db, db + LO8, KS_K, LBO_K, SBO_K,
                                                      vb, vb + LO8, KS_K, LBO_K, SBO_K, id_kk_s, n > 0, LAY, LAY);
@@ -231,7 +296,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                     CCA_STAMP(2);
                 }
                 commit_to(&bars[B_DP_FULL]);
-                if (k + 1 < nk) issue_s(k + 1);                   // overlaps the dS computation of this line
+                if (k + 1 < nk) issue_s(k + 1);                   // overlaps the dS computation of this item
                 // ---- phase D: dQ = dS K,  dK = dS^T Q      (dS in the P planes)
                 mbar_wait(&bars[B_DS_FULL], k & 1);
                 CCA_STAMP(2);
@@ -260,68 +325,104 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
         } else if (warp == kWarpStore) {
             // =============================== store warp (one lane): the output staging slot <-> global ===============================
             if (lane == 0) {
-                const uint32_t total = (uint32_t)nk * NO;
                 uint8_t *slot = smem + S::off_out;
-                const uint64_t pol_keep = p.hints ? l2_policy_evict_last() : l2_policy_evict_normal();
-                const uint64_t pol_stream = p.hints ? l2_policy_evict_first() : l2_policy_evict_normal();
-                for (uint32_t c = 0; c < total; ++c) {
-                    const int k = c / NO, i = c - k * NO;
-                    int cw, ch, cb;
-                    line_coords(line_of(k), cw, ch, cb);
-                    // slot is free once the previous store has been read out of shared memory
-                    tma_store_wait_read<0>();
-                    mbar_arrive(&bars[B_OUT_FULL]);
-                    mbar_wait(&bars[B_STAGED], c & 1);
-                    if (p.sync && !p.col) {
-                        // overlapped row pass: all column lines of this sample must have landed before we accumulate
-                        if (i == 0) { wait_count(p.done + cb, (unsigned)p.W); fence_proxy_async_global(); }
-                    } else if (c == 0) {
-                        pdl_wait();
+                pdl_wait();                                // prep kernel complete: counters and the first samples of dq/dk/dv cleared
+                int pending = -1;
+                uint32_t c = 0;
+                for (int k = 0; k < nk; ++k) {
+                    const Item it = item_of(k);
+                    const int zb = it.b + p.ahead;
+                    if (zb < p.sp.B) {                     // zero-ahead: this item's share of sample zb (dq, dk, dv)
+                        uint8_t *dst[3] = {p.dq + (long)zb * p.sb_q, p.dk + (long)zb * p.sb_q, p.dv + (long)zb * p.sb_v};
+                        for (int t = 0; t < 3; ++t) {
+                            const long sh = t < 2 ? p.share_q : p.share_v, sb = t < 2 ? p.sb_q : p.sb_v;
+                            const long lo = (long)it.j * sh;
+                            const long hi = lo + sh < sb ? lo + sh : sb;
+                            for (long o = lo; o < hi; o += kZeroBuf)
+                                bulk_store(dst[t] + o, smem + S::off_zero, (uint32_t)(hi - o < kZeroBuf ? hi - o : kZeroBuf));
+                        }
+                        tma_store_commit();
+                        pending = zb;
                     }
-                    if (p.col) {                                   // column pass defines dq/dk/dv ...
-                        const uint64_t pol = cb >= p.keep_from ? pol_keep : pol_stream;
-                        tma_store_4d(out_map(i), slot, out_c0(i), cw, ch, cb, pol);
-                        if constexpr (!BF) tma_store_4d(out_map(i), slot + T::kTile, out_c0(i) + 32, cw, ch, cb, pol);
-                    } else {                                       // ... the row pass accumulates onto them (TMA reduce-add at L2)
-                        tma_reduce_add_4d(out_map(i), slot, out_c0(i), cw, ch, cb, pol_stream);
-                        if constexpr (!BF) tma_reduce_add_4d(out_map(i), slot + T::kTile, out_c0(i) + 32, cw, ch, cb, pol_stream);
-                    }
-                    tma_store_commit();
-                    if (p.sync && p.col && i == 0 && k > 0) {
-                        // publish the previous line: its stores were committed at least one chunk period ago, so waiting for
-                        // everything but the group just committed costs (almost) nothing
-                        int pw, ph2, pb;
-                        line_coords(line_of(k - 1), pw, ph2, pb);
-                        tma_store_wait_all<1>();
-                        fence_proxy_async_global();
-                        __threadfence();
-                        atomicAdd(p.done + pb, 1u);
+                    for (int i = 0; i < NO; ++i, ++c) {
+                        // output tile i of the item: i < NCH -> dV chunk i (rows = key pixels); NCH -> dQ (query pixels); NCH+1 -> dK
+                        const CUtensorMap *m = i < NCH ? (it.col ? &mdvc : &mdvr) : (i == NCH ? (it.col ? &mdqc : &mdqr) : (it.col ? &mdkc : &mdkr));
+                        const int c0 = i < NCH ? i * kNC : 0;
+                        const int start = i == NCH ? it.q0 : it.k0;
+                        const int cw = it.col ? it.line : start, ch = it.col ? start : it.line;
+                        // slot is free once the previous store has been read out of shared memory
+                        tma_store_wait_read<0>();
+                        mbar_arrive(&bars[B_OUT_FULL]);
+                        mbar_wait(&bars[B_STAGED], c & 1);
+                        if (i == 0) {
+                            if (pending >= 0) {
+                                tma_store_wait_all<0>();
+                                publish_count(p.zdone + pending);
+                                pending = -1;
+                            }
+                            if (it.b >= p.ahead) {
+                                wait_count(p.zdone + it.b, (unsigned)p.sp.per_sample);
+                                fence_proxy_async_all();
+                            }
+                        }
+                        tma_reduce_add_4d(m, slot, c0, cw, ch, it.b);
+                        if constexpr (!BF) tma_reduce_add_4d(m, slot + T::kTile, c0 + 32, cw, ch, it.b);
+                        tma_store_commit();
                     }
                 }
                 tma_store_wait_all<0>();
-                if (p.sync && p.col && nk > 0) {
-                    int pw, ph2, pb;
-                    line_coords(line_of(nk - 1), pw, ph2, pb);
-                    fence_proxy_async_global();
-                    __threadfence();
-                    atomicAdd(p.done + pb, 1u);
-                }
+                if (pending >= 0) publish_count(p.zdone + pending);
             }
         }
     } else if (warp >= kWarpConv0) {
         // =============================== converters (256 threads) ===============================
         reg_dec<kRegsConvB>();
         const int t = tid - kWarpConv0 * 32;
-        const uint32_t total = BF ? 0u : (uint32_t)nk * NI;         // bf16 tiles need no conversion
         int dbg_n = t == 0 ? 0 : 512;
-        for (uint32_t g = 0; g < total; ++g) {
-            const int slot = g % kNLd;
-            mbar_wait(&bars[B_LD_FULL + slot], (g / kNLd) & 1);
-            CCA_STAMP(1);
-            if constexpr (!BF) convert_slot_inplace<LK>(smem + S::off_ld + slot * T::kSlot, t);
-            fence_proxy_async();
-            mbar_arrive(&bars[B_OP_FULL + slot]);
-            CCA_STAMP(1);
+        (void)dbg_n;
+        uint32_t g = 0, ncalc = 0;
+        // every ring slot passes through the converters (bf16 tiles only for the hand-shake: OP_FULL is what the MMA warp
+        // waits for in both dtypes, so a slot the converters read for delta is never released before they are done)
+        auto conv = [&](int count) {
+            for (int e = 0; e < count; ++e, ++g) {
+                const int slot = g % kNLd;
+                mbar_wait(&bars[B_LD_FULL + slot], (g / kNLd) & 1);
+                CCA_STAMP(1);
+                if constexpr (!BF) {
+                    convert_slot_inplace<LK>(smem + S::off_ld + slot * T::kSlot, t);
+                    fence_proxy_async();
+                }
+                mbar_arrive(&bars[B_OP_FULL + slot]);
+                CCA_STAMP(1);
+            }
+        };
+        if (nk > 0) conv(2);
+        for (int k = 0; k < nk; ++k) {
+            const bool calc = calc_delta(p, item_of(k));
+            float dacc = 0.f;
+            for (int n = 0; n < NCH; ++n) {
+                conv(1);                                               // V
+                if (calc) {                                            // dO + O: dot products, then dO as operand
+                    const int sd = g % kNLd, so = (g + 1) % kNLd;
+                    mbar_wait(&bars[B_LD_FULL + sd], (g / kNLd) & 1);
+                    mbar_wait(&bars[B_LD_FULL + so], ((g + 1) / kNLd) & 1);
+                    dacc += convert_dot<LK, BF>(smem + S::off_ld + sd * T::kSlot, smem + S::off_ld + so * T::kSlot, t, &bars[B_LD_EMPTY + so]);
+                    fence_proxy_async();
+                    mbar_arrive(&bars[B_OP_FULL + sd]);
+                    mbar_arrive(&bars[B_OP_FULL + so]);                // nobody waits for it; keeps the slot's phase in step
+                    g += 2;
+                } else {
+                    conv(1);                                           // dO
+                }
+            }
+            if (calc) {                                                // hand the per-pixel sums to the P/dS group
+                mbar_wait(&bars[B_DELTA_EMPTY], (ncalc & 1) ^ 1);
+                dpart[(t >> 7) * 128 + (t & 127)] = dacc;
+                mbar_arrive(&bars[B_DELTA_FULL]);
+                ++ncalc;
+            }
+            if (k + 1 < nk) conv(2);
+            conv(2);
         }
     } else if (warp >= 4) {
         // =============================== P / dS group (128 threads, TMEM lane == query pixel) ===============================
@@ -329,17 +430,16 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
         const int r = tid - 128;
         const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         int dbg_n = r == 0 ? 0 : 512;
+        (void)dbg_n;
+        uint32_t ncalc = 0;
+        pdl_wait();                                                   // counters / delta buffer belong to this call from here on
         for (int k = 0; k < nk; ++k) {
-            int cw, ch, cb;
-            line_coords(line_of(k), cw, ch, cb);
-            const bool rvalid = r < p.L;
-            float lse2 = 0.f, dl = 0.f;
-            if (rvalid) {
-                const long pix = p.col ? ((long)cb * p.H + r) * p.W + cw : ((long)cb * p.H + ch) * p.W + r;
-                lse2 = p.lse[pix] * kLog2e;
-                if (p.col) pdl_wait();                 // delta comes from the kernel right before the column pass
-                dl = p.delta[pix];
-            }
+            const Item it = item_of(k);
+            const bool calc = calc_delta(p, it);
+            const bool rvalid = r < it.lq;
+            const long pix = item_pixel(p.sp, it, rvalid ? r : 0);
+            const float lse2 = rvalid ? p.lse[pix] * kLog2e : 0.f;
+            const int self = it.col ? it.q0 + r - it.k0 : -1;
             uint8_t *ph = smem + S::off_p + r * 16, *pl = ph + T::kPP * T::kPlane;
             // ---------------- P = exp(S - lse)
             const uint32_t tsd = tl + (k & 1) * 128;           // S(k) / dP(k) buffer
@@ -362,7 +462,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
                     const int j = c0 + e;
-                    const bool ok = rvalid && j < p.L && !(p.col && j == r);
+                    const bool ok = rvalid && j < it.lk && j != self;
                     s[e] = ok ? exp2f(s[e] * kLog2e - lse2) : 0.f;
                 }
                 if (r < LK) {
@@ -386,6 +486,22 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
             fence_proxy_async();
             mbar_arrive(&bars[B_P_FULL]);
             CCA_STAMP(3);
+            // ---------------- delta of this query pixel
+            float dl = 0.f;
+            if (calc) {
+                mbar_wait(&bars[B_DELTA_FULL], ncalc & 1);
+                dl = dpart[r] + dpart[128 + r];
+                mbar_arrive(&bars[B_DELTA_EMPTY]);
+                ++ncalc;
+                if (p.delta_mode == 1) {                       // publish for the other items of the sample
+                    if (rvalid) p.delta[pix] = dl;
+                    named_bar_sync(2, 128);
+                    if (r == 0) { __threadfence(); atomicAdd(p.ddone + it.b, 1u); }
+                }
+            } else {
+                wait_count(p.ddone + it.b, (unsigned)p.sp.seg0);
+                if (rvalid) dl = __ldcg(p.delta + pix);
+            }
             // ---------------- dS = P * (dP - delta)   (all MMAs that read P have completed: DP_FULL is committed after them)
             mbar_wait(&bars[B_DP_FULL], k & 1);
             tc_fence_after();
@@ -410,8 +526,9 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const float p0 = bf_lo(hw[e]) + bf_lo(lw[e]), p1 = bf_hi(hw[e]) + bf_hi(lw[e]);
-                            ds[2 * e] = p0 * (dp[h * 8 + 2 * e] - dl);
-                            ds[2 * e + 1] = p1 * (dp[h * 8 + 2 * e + 1] - dl);
+                            // P == 0 marks a masked / padded entry: its dP may hold anything (rows of a neighbouring tile)
+                            ds[2 * e] = p0 != 0.f ? p0 * (dp[h * 8 + 2 * e] - dl) : 0.f;
+                            ds[2 * e + 1] = p1 != 0.f ? p1 * (dp[h * 8 + 2 * e + 1] - dl) : 0.f;
                         }
                         if constexpr (BF) {
                             *reinterpret_cast<uint4 *>(ph + kc * T::kPlane) =
@@ -439,11 +556,12 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
         uint8_t *slot = smem + S::off_out;
         uint32_t oc = 0;
         int dbg_n = tid == 0 ? 0 : 512;
+        (void)dbg_n;
         for (int k = 0; k < nk; ++k) {
             for (int i = 0; i < NO; ++i, ++oc) {
                 const int ob = oc & 1;
                 CCA_STAMP(4);
-                mbar_wait(&bars[B_OUT_FULL], oc & 1);                 // staging slot free / column partial landed
+                mbar_wait(&bars[B_OUT_FULL], oc & 1);                 // staging slot free
                 mbar_wait(&bars[B_O_FULL + ob], (oc >> 1) & 1);
                 tc_fence_after();
                 CCA_STAMP(4);
@@ -453,7 +571,9 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(&bars[B_O_EMPTY + ob]);
-                if (r < p.L) {                                        // rows >= L are clipped by the TMA store
+                // rows beyond the tile are exact zeros (P and dS are zero there): inside the image they add nothing, outside the
+                // TMA clips them
+                if (r < LK) {
                     uint8_t *row = slot + r * 128;
                     const int sw = r & 7;
                     if constexpr (BF) {
@@ -480,81 +600,59 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant_
     if (warp == 0) tmem_dealloc<kTmemCols>(tmem);
 }
 
-// delta[pix] = sum_c dout[pix][c] * out[pix][c]   (channels-last: one warp per pixel, float4 lanes)
-__global__ void __launch_bounds__(256) cca_delta_nhwc_kernel(const float4 *__restrict__ dout, const float4 *__restrict__ out,
-                                                             float *__restrict__ delta, long npix, int c4)
-{
-    // pixels are walked backwards: the column pass starts with sample 0, whose dout is then the most recent data in L2
-    pdl_launch_dependents();
-    const long pix = npix - 1 - ((long)blockIdx.x * 8 + (threadIdx.x >> 5));
-    if (pix < 0) return;
-    const int lane = threadIdx.x & 31;
-    const float4 *a = dout + pix * c4, *b = out + pix * c4;
-    float s = 0.f;
-    for (int i = lane; i < c4; i += 32) {
-        const float4 x = __ldg(a + i), y = __ldg(b + i);
-        s += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) delta[pix] = s;
-}
-
-// bf16 variant: 8 channels per 16-byte load
-__global__ void __launch_bounds__(256) cca_delta_nhwc_bf16_kernel(const uint4 *__restrict__ dout, const uint4 *__restrict__ out,
-                                                                  float *__restrict__ delta, long npix, int c8)
+// Prologue of the backward: clears the first `head` samples of dq, dk, dv and the per-sample counters.
+__global__ void __launch_bounds__(256) cca_bwd_prep_kernel(uint4 *dq, uint4 *dk, uint4 *dv, long nq16, long nv16,
+                                                           unsigned int *counters, int n_counters)
 {
     pdl_launch_dependents();
-    const long pix = npix - 1 - ((long)blockIdx.x * 8 + (threadIdx.x >> 5));
-    if (pix < 0) return;
-    const int lane = threadIdx.x & 31;
-    const uint4 *a = dout + pix * c8, *b = out + pix * c8;
-    float s = 0.f;
-    for (int i = lane; i < c8; i += 32) {
-        const uint4 x = __ldg(a + i), y = __ldg(b + i);
-        const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) s += bf_lo(xw[e]) * bf_lo(yw[e]) + bf_hi(xw[e]) * bf_hi(yw[e]);
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) delta[pix] = s;
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long)gridDim.x * blockDim.x;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (long i = tid; i < nq16; i += nth) { dq[i] = z; dk[i] = z; }
+    for (long i = tid; i < nv16; i += nth) dv[i] = z;
+    for (long i = tid; i < n_counters; i += nth) counters[i] = 0u;
 }
 
 long long *g_bwd_dbg = nullptr;
 
 template <int LK, bool BF>
-cudaError_t launch_bwd_pass(const void *dout, const void *q, const void *k, const void *v, const float *lse, const float *delta,
-                            void *dq, void *dk, void *dv, unsigned int *done, int sync, Dims d, bool col, cudaStream_t st,
-                            const char **why)
+cudaError_t launch_bwd(const void *dout, const void *q, const void *k, const void *v, const void *out, const float *lse, float *delta,
+                       unsigned int *counters, void *dq, void *dk, void *dv, Dims d, int ahead, int delta_mode, cudaStream_t st,
+                       const char **why)
 {
-    CUtensorMap mq, mk, mv, mdo, mdq, mdk, mdv;
-    const bool ok = make_map(&mq, q, d.B, d.H, d.W, d.Cq, LK, col, BF) && make_map(&mk, k, d.B, d.H, d.W, d.Cq, LK, col, BF) &&
-                    make_map(&mv, v, d.B, d.H, d.W, d.C, LK, col, BF) && make_map(&mdo, dout, d.B, d.H, d.W, d.C, LK, col, BF) &&
-                    make_map(&mdq, dq, d.B, d.H, d.W, d.Cq, LK, col, BF) && make_map(&mdk, dk, d.B, d.H, d.W, d.Cq, LK, col, BF) &&
-                    make_map(&mdv, dv, d.B, d.H, d.W, d.C, LK, col, BF);
-    if (!ok) {
-        if (why) *why = "cuTensorMapEncodeTiled failed";
-        return cudaErrorInvalidValue;
-    }
+    CUtensorMap m[16];
+    const void *base[8] = {q, k, v, dout, out, dq, dk, dv};
+    const int ch[8] = {d.Cq, d.Cq, d.C, d.C, d.C, d.Cq, d.Cq, d.C};
+    for (int t = 0; t < 8; ++t)
+        for (int r = 0; r < 2; ++r)
+            if (!get_map(&m[2 * t + r], base[t], d.B, d.H, d.W, ch[t], LK, r == 0, BF)) {
+                if (why) *why = "cuTensorMapEncodeTiled failed";
+                return cudaErrorInvalidValue;
+            }
     BwdParams p;
-    p.B = d.B; p.H = d.H; p.W = d.W; p.C = d.C; p.Cq = d.Cq;
-    p.L = col ? d.H : d.W; p.NL = col ? d.W : d.H; p.col = col ? 1 : 0;
+    p.sp = make_space(d.B, d.H, d.W);
+    p.C = d.C; p.Cq = d.Cq;
+    p.npix = (long)d.B * d.H * d.W;
     p.lse = lse; p.delta = delta;
-    p.done = done; p.sync = sync;
-    {   // per sample the row pass re-reads q,k,v,dout and accumulates onto dq,dk,dv
-        const double per_sample = (4.0 * d.Cq + 3.0 * d.C) * d.H * d.W * (BF ? 2 : 4);
-        int keep = (int)(tc_l2_keep_mb() * 1e6 / per_sample);
-        if (keep > d.B) keep = d.B;
-        p.hints = tc_l2_hints();
-        p.keep_from = d.B - keep;
-    }
-    p.dbg = g_bwd_dbg ? g_bwd_dbg + (col ? 0 : 2560) : nullptr;
-    auto kern = cca_tc_bwd_kernel<LK, BF>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<LK, BF>::kBytes);
+    p.zdone = counters; p.ddone = counters + d.B;
+    p.delta_mode = delta_mode;
+    p.dq = reinterpret_cast<uint8_t *>(dq); p.dk = reinterpret_cast<uint8_t *>(dk); p.dv = reinterpret_cast<uint8_t *>(dv);
+    const long es = BF ? 2 : 4;
+    p.sb_q = (long)d.H * d.W * d.Cq * es; p.sb_v = (long)d.H * d.W * d.C * es;
+    p.share_q = zero_share_bytes(p.sb_q, p.sp.per_sample); p.share_v = zero_share_bytes(p.sb_v, p.sp.per_sample);
+    p.ahead = ahead;
+    p.dbg = g_bwd_dbg;
+    // prologue: counters and the first `ahead` samples of the outputs
+    const int head = ahead < d.B ? ahead : d.B;
+    cca_bwd_prep_kernel<<<sm_count(), 256, 0, st>>>(reinterpret_cast<uint4 *>(dq), reinterpret_cast<uint4 *>(dk), reinterpret_cast<uint4 *>(dv),
+                                                    head * p.sb_q / 16, head * p.sb_v / 16, counters, 2 * d.B);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    const int lines = d.B * p.NL;
-    const int grid = lines < sm_count() ? lines : sm_count();
+    auto kern = cca_tc_bwd_kernel<LK, BF>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<LK, BF>::kBytes);
+    if (e != cudaSuccess) return e;
+    const int sms = sm_count();
+    const int grid = p.sp.total < sms ? p.sp.total : sms;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = BwdSmem<LK, BF>::kBytes; cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -562,7 +660,8 @@ cudaError_t launch_bwd_pass(const void *dout, const void *q, const void *k, cons
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = tc_pdl() ? 1 : 0;
-    e = cudaLaunchKernelEx(&cfg, kern, mq, mk, mv, mdo, mdq, mdk, mdv, p);
+    e = cudaLaunchKernelEx(&cfg, kern, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], m[11], m[12], m[13],
+                           m[14], m[15], p);
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();
 }
@@ -573,40 +672,32 @@ void set_tc_bwd_debug_buffer(void *p) { g_bwd_dbg = reinterpret_cast<long long *
 
 bool tc_backward_supported(Dims d, int dtype) { return tc::shape_supported(d, dtype); }
 
-// all tensors channels-last (NHWC), fp32 or bf16; ws = delta [B,H,W]
+// Workspace of the backward: delta [B,H,W] fp32, then 2*B unsigned counters.
+size_t tc_backward_workspace(Dims d)
+{
+    const size_t delta = ((size_t)d.B * d.H * d.W * sizeof(float) + 15) & ~(size_t)15;
+    return delta + (((size_t)2 * d.B * sizeof(unsigned int) + 15) & ~(size_t)15);
+}
+
+// all tensors channels-last (NHWC), fp32 or bf16
 cudaError_t tc_backward(const void *dout, const void *q, const void *k, const void *v, const void *out, const float *lse,
                         void *dq, void *dk, void *dv, void *ws, Dims d, int dtype, cudaStream_t st, const char **why)
 {
     float *delta = reinterpret_cast<float *>(ws);
-    const long npix = (long)d.B * d.H * d.W;
+    const size_t delta_bytes = ((size_t)d.B * d.H * d.W * sizeof(float) + 15) & ~(size_t)15;
+    unsigned int *counters = reinterpret_cast<unsigned int *>(reinterpret_cast<uint8_t *>(ws) + delta_bytes);
+    const ItemSpace sp = make_space(d.B, d.H, d.W);
+    const int lk = lk_for(max_tile(sp));
     const bool bf = dtype == CCA_BF16;
-    const unsigned dgrid = (unsigned)((npix + 7) / 8);
-    // tc_pdl() == 2: the row pass overlaps the tail of the column pass; per-sample completion counters (behind delta in ws)
-    unsigned int *done = reinterpret_cast<unsigned int *>(delta + npix);
-    const int sync = tc_pdl() == 2 ? 1 : 0;
-    if (sync) {
-        cudaError_t e0 = cudaMemsetAsync(done, 0, sizeof(unsigned int) * d.B, st);
-        if (e0 != cudaSuccess) return e0;
-    }
+    int ahead = tc_zero_ahead();
+    if (ahead < 1) ahead = 1;
+    int mode = tc_delta_mode();                       // -1: automatic
+    if (mode < 0) mode = (sp.col.nt == 1 && sp.row.nt == 1) ? 1 : 0;
     if (bf)
-        cca_delta_nhwc_bf16_kernel<<<dgrid, 256, 0, st>>>(reinterpret_cast<const uint4 *>(dout), reinterpret_cast<const uint4 *>(out),
-                                                          delta, npix, d.C / 8);
-    else
-        cca_delta_nhwc_kernel<<<dgrid, 256, 0, st>>>(reinterpret_cast<const float4 *>(dout), reinterpret_cast<const float4 *>(out),
-                                                     delta, npix, d.C / 4);
-    count_launch();
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    auto go = [&](int lk, bool col) {
-        if (bf)
-            return lk == 80 ? launch_bwd_pass<80, true>(dout, q, k, v, lse, delta, dq, dk, dv, done, sync, d, col, st, why)
-                            : launch_bwd_pass<112, true>(dout, q, k, v, lse, delta, dq, dk, dv, done, sync, d, col, st, why);
-        return lk == 80 ? launch_bwd_pass<80, false>(dout, q, k, v, lse, delta, dq, dk, dv, done, sync, d, col, st, why)
-                        : launch_bwd_pass<112, false>(dout, q, k, v, lse, delta, dq, dk, dv, done, sync, d, col, st, why);
-    };
-    e = go(lk_for(d.H), true);
-    if (e != cudaSuccess) return e;
-    return go(lk_for(d.W), false);
+        return lk == 80 ? launch_bwd<80, true>(dout, q, k, v, out, lse, delta, counters, dq, dk, dv, d, ahead, mode, st, why)
+                        : launch_bwd<112, true>(dout, q, k, v, out, lse, delta, counters, dq, dk, dv, d, ahead, mode, st, why);
+    return lk == 80 ? launch_bwd<80, false>(dout, q, k, v, out, lse, delta, counters, dq, dk, dv, d, ahead, mode, st, why)
+                    : launch_bwd<112, false>(dout, q, k, v, out, lse, delta, counters, dq, dk, dv, d, ahead, mode, st, why);
 }
 
 }  // namespace cca

@@ -188,22 +188,18 @@ inline bool make_map(CUtensorMap *m, const void *base, int B, int H, int W, int 
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-inline int lk_for(int L) { return L <= 80 ? 80 : (L <= 112 ? 112 : 0); }
-inline int sm_count()
-{
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return n;
-}
+// LK template (padded tile length) for the longest tile of a problem
+inline int lk_for(int tile) { return tile <= 80 ? 80 : (tile <= 112 ? 112 : 0); }
+// Cached tensor maps (cca_tc_host.cu): encoding costs ~1 us of driver time per map and an op call needs 8-15 of them;
+// a map only depends on (base, shape, box, dtype), so it stays valid for as long as that address holds such a tensor.
+bool get_map(CUtensorMap *m, const void *base, int B, int H, int W, int C, int LK, bool col, bool bf16);
+// SM count of the CURRENT device (cached per device id)
+int sm_count();
 inline bool shape_supported(Dims d, int dtype)
 {
     if (dtype != CCA_F32 && dtype != CCA_BF16) return false;
     if (d.Cq % 16 != 0 || d.Cq > 64 || d.Cq < 16 || d.C % kNC != 0) return false;
-    if (lk_for(d.H) == 0 || lk_for(d.W) == 0) return false;
+    if (d.H > 112 * 8 || d.W > 112 * 8) return false;        // cca_items.cuh: at most kMaxNT tiles of kMaxTile pixels per line
     return get_encode() != nullptr;
 }
 

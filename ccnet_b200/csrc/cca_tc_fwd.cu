@@ -1,32 +1,38 @@
-// tcgen05 / TMA forward kernel of criss-cross attention for sm_100a (channels-last tensors).
+// tcgen05 / TMA forward (values) kernel of criss-cross attention for sm_100a (channels-last tensors).
 //
-// Layout: q,k [B,H,W,Cq], v,out [B,H,W,C] (torch channels_last).  In this layout an image row and an
-// image column are the same object -- L pixels with a fixed pixel stride, each pixel's channels
-// contiguous -- so ONE kernel serves both branches of cc_attention/functions.py:38-47:
-//   column items (self entry masked, functions.py:38): out <- V P_c / l_c, stats <- (m_c, l_c)
-//   row items    (functions.py:39): flash-style merge with the column result -> out, lse  (functions.py:40-47)
+// Layout: q,k [B,H,W,Cq], v,out [B,H,W,C] (torch channels_last).  In this layout an image row and an image column are
+// the same object -- L pixels with a fixed pixel stride, each pixel's channels contiguous -- so one kernel serves both
+// branches of cc_attention/functions.py:38-47.
 //
-// ONE persistent launch processes both kinds of items: the item list is  col(0) | col(1) row(0) | col(2) row(1) ...
-// (all column lines of a sample; its row lines one block later), CTA c takes items c, c+grid, ...  A row line of
-// sample b needs every column line of b: column items bump a per-sample counter after their last TMA store
-// has completed; row items spin on it (all earlier items are owned by running CTAs, so this cannot deadlock).
-// Scheduling a sample's rows shortly after its columns keeps q,k,v and the partial output in the 126 MB L2.
+// Formulation: the statistics pre-pass (cca_tc_stats.cu) has left the log-sum-exp of every pixel's logits
+// per (direction, key block).  An item (cca_items.cuh: direction, sample, line, query tile, key block) combines those few
+// planes into the pixel's final lse and computes its share of the output with the FINAL normalisation,
+//     P = exp(S - lse)        O_item = P V_block        out[query pixels] += O_item      (TMA reduce-add, at L2)
+// so items never exchange anything: no partial output is written and read back, no per-pixel merge, and lines longer
+// than one tile are just more items.  ONE persistent launch walks the items sample by sample: the second direction of a
+// sample finds q,k,v in L2 and adds onto output lines that are still L2-resident, so DRAM sees q,k,v once and out once.
+//
+// Zero-ahead: `out` needs no initialisation by the caller.  The statistics kernel clears the first `ahead` samples; every
+// item of sample b clears 1/per_sample of sample b+ahead (bulk copies of a zero tile, issued by the store warp before the
+// item's first store) and bumps zdone[b+ahead] once those copies have completed; the first reduce-add of an item of sample
+// b waits for zdone[b] == per_sample.  Only items with a LOWER index are ever waited for, and each persistent CTA walks its
+// items in increasing order, so the wait cannot cycle.  The two contributions of a pixel (column item, row item) are added
+// onto an exact zero: the result does not depend on their order (bit-reproducible); with key-block tiling (lines > 112
+// pixels) a pixel gets 2*nt contributions whose order is not fixed (last-bit differences between runs).
 //
 // Roles (warpgroups, registers rebalanced with setmaxnreg), software-pipelined across items:
-//   TMA producer (1 thread)   : 4-D tiled loads [LK px][32 ch] fp32, SWIZZLE_128B, OOB pixels zero-filled,
-//                               3-slot ring: Q, K of the NEXT item, then the V chunks (64 ch) of the current.
-//   converter warps (256 thr) : fp32 -> bf16 hi + bf16 lo split (x = hi + lo to ~2^-17), written as UMMA
-//                               canonical no-swizzle operand planes [8-channel chunk][pixel][16 B].
-//   MMA warp (elect.sync)     : S = Q K^T (SS, 3 bf16 MMAs per k-step: hi*hi + hi*lo + lo*hi, fp32 in TMEM),
-//                               then per V chunk O = P V with A = P read from TMEM (TS): the probabilities
-//                               never touch shared memory, so the MMA is not SMEM-bandwidth bound.
-//   softmax group (128 thr)   : TMEM -> registers (one query pixel per thread), exp2 softmax, P split hi/lo
-//                               and written back to TMEM as packed bf16 pairs, per-pixel scales / stats / lse.
-//   epilogue group (128 thr)  : per V chunk TMEM -> scale/merge -> swizzled smem tile -> TMA store
-//                               (3 staging slots; the column partial is prefetched into the slot by TMA).
-// All hand-offs are mbarriers (TMA complete_tx, tcgen05.commit, thread arrives).
-#include <cstdlib>
-
+//   TMA producer (1 thread)   : 4-D tiled loads [LK px][32 ch] fp32 / [LK px][64 ch] bf16, SWIZZLE_128B, OOB pixels
+//                               zero-filled; ring of 5 (6) slots: Q, K of the NEXT item are slipped in after the first V
+//                               chunks of the current one.
+//   converter warps (256 thr) : fp32 only: fp32 -> bf16 hi + lo (x = hi + lo to ~2^-17), in place, as UMMA canonical
+//                               no-swizzle operand planes [8-channel chunk][pixel][16 B].
+//   MMA warp (elect.sync)     : S = Q K^T (SS; 3 bf16 MMAs per k-step for fp32 I/O), then per 64-channel V chunk
+//                               O = P V with A = P read from TMEM (TS), fp32 accumulation in TMEM.
+//   softmax group (128 thr)   : one pass over the S row in TMEM (lane = query pixel): P = exp2(S log2e - lse2) -> TMEM as
+//                               packed bf16 (hi/lo); also writes the final lse (row items, first key block).
+//   epilogue group (128 thr)  : per chunk TMEM -> swizzled staging tile (no scaling left to do).
+//   store warp (1 lane)       : zero-ahead, TMA reduce-add of the staged tiles, counters.
+#include "cca_items.cuh"
 #include "cca_tc_common.cuh"
 
 namespace cca {
@@ -35,112 +41,50 @@ using namespace tc;
 
 constexpr int kTmemCols = 512;      // S [0,128)   P double buffer (hi/lo) [128,256) [256,384)   O ring 2 x 64 [384,512)
 constexpr int kTmemP = 128, kTmemO = 384, kNOB = 2;
-// the in-place conversion keeps a whole 128 B row (split into hi/lo) live across a barrier: converters get 88 registers; the
-// softmax group streams its row from TMEM 16 columns at a time and needs few
 constexpr int kRegsSoft = 104, kRegsEpi = 128, kRegsConvF = 88;
 static_assert(reg_pool_ok(kRegsSoft, kRegsEpi, kRegsConvF), "setmaxnreg pool");
-constexpr int kNOut = 3;            // staging slots
-constexpr int kNLdMax = 6;          // load ring: 5 slots (fp32: 28 KB each, converted to bf16 hi/lo planes IN PLACE) or 6 (bf16: 14 KB each)
-
-enum { MODE_FUSED = 0, MODE_DYNAMIC = 1, MODE_COL_ONLY = 2, MODE_ROW_ONLY = 3 };
+constexpr int kNOut = 2;            // staging slots
+constexpr int kZeroBuf = 2048;      // zero tile for the zero-ahead bulk copies
 
 struct FwdParams {
-    int B, H, W, C, Cq;
-    int mode;              // MODE_DYNAMIC: one launch, lines claimed from two global queues (a row line only once its
-                           // sample's column lines are complete); MODE_FUSED: one launch, static interleaved order;
-                           // *_ONLY: one pass per launch
-    unsigned int *sched;   // [0] next column line to hand out, [1] first sample that may still have row lines (MODE_DYNAMIC)
-    unsigned int *rown;    // [B] next row line of each sample (MODE_DYNAMIC)
-    float2 *stats;         // [B,H,W] (m_c, l_c) of the column branch
-    float *lse;            // [B,H,W]
-    unsigned int *done;    // [B] column lines completed (MODE_FUSED only)
-    int sync;              // two launches, the row pass overlapping the tail of the column pass (programmatic dependent launch):
-                           // column lines are counted in done[] as in the fused modes and a row line waits for its own sample only
-    int hints;             // L2 eviction hints on the bulk copies: column lines of samples >= keep_from are kept (evict_last:
-    int keep_from;         // the row pass, which walks the samples backwards, finds them in L2), everything else streams
-    long long *dbg;        // optional timeline buffer (4 roles x 512 stamps), CTA 0 only; nullptr in production
+    ItemSpace sp;
+    int C, Cq;
+    long npix;
+    const float *parts;    // [nparts][B*H*W] partial log2-sum-exp2 (statistics pre-pass)
+    float *lse;            // [B,H,W] natural-log lse (saved for backward)
+    unsigned int *zdone;   // [B] zero shares of sample b completed
+    uint8_t *out;          // base of the output tensor (bytes)
+    long sample_bytes;     // H*W*C*esize
+    long share;            // zero share per item (bytes, multiple of 128)
+    int ahead;             // zero-ahead distance in samples (>= 1)
+    long long *dbg;        // optional timeline buffer (CTA 0), -DCCA_TIMELINE builds only
 };
 
-struct Item { int col, b, i, L; };
-
-__device__ __forceinline__ int total_items(const FwdParams &p)
-{
-    return p.mode <= MODE_DYNAMIC ? p.B * (p.W + p.H) : (p.mode == MODE_COL_ONLY ? p.B * p.W : p.B * p.H);
-}
-__device__ __forceinline__ Item decode_item(const FwdParams &p, int idx)
-{
-    Item it;
-    if (p.mode == MODE_FUSED) {
-        // order: col(0) | col(1) row(0) | col(2) row(1) | ... | row(B-1)  -- the rows of a sample trail its columns by one
-        // block of column lines, so a row line (almost) never has to wait for the column lines it depends on, while
-        // the partial output and q,k,v of the sample are still in L2
-        if (idx < p.W) { it.col = 1; it.b = 0; it.i = idx; }
-        else {
-            const int per = p.W + p.H, x = idx - p.W;
-            const int j = x / per, rem = x - j * per;
-            if (j < p.B - 1 && rem < p.W) { it.col = 1; it.b = j + 1; it.i = rem; }
-            else if (j < p.B - 1) { it.col = 0; it.b = j; it.i = rem - p.W; }
-            else { it.col = 0; it.b = p.B - 1; it.i = rem; }
-        }
-    } else {
-        it.col = p.mode == MODE_COL_ONLY;
-        const int nl = it.col ? p.W : p.H;
-        it.b = idx / nl;
-        it.i = idx - it.b * nl;
-        // the row pass walks the samples backwards: what the column pass touched last (v, q, k and the partial output of
-        // the last samples) is still in L2 when the row pass starts
-        if (!it.col && !p.sync) it.b = p.B - 1 - it.b;       // (an overlapped row pass starts with the samples completed first)
-    }
-    it.L = it.col ? p.H : p.W;
-    return it;
-}
-
+#ifdef CCA_TIMELINE
 #define CCA_STAMP(role)                                                                          \
     do {                                                                                         \
         if (p.dbg && blockIdx.x == 0 && dbg_n < 512) p.dbg[(role) * 512 + dbg_n++] = clock64();  \
     } while (0)
+#else
+#define CCA_STAMP(role) do { } while (0)
+#endif
 
 template <int LK, bool BF> struct FwdSmem {
     using T = Tiles<LK, BF>;
-    static constexpr int kNLd = BF ? 6 : 5;
+    static constexpr int kNLd = BF ? 8 : 6;
     static constexpr int off_ld = 0;                          // kNLd load slots; every slot is the UMMA operand itself: a bf16 tile as
                                                               // loaded, an fp32 tile once the converters have rewritten it in place
-    static constexpr int off_out = off_ld + kNLd * T::kSlot;  // kNOut out slots
-    static constexpr int off_tail = off_out + kNOut * T::kSlot; // pad: an M=128 MMA reads (128 - LK) rows past the last plane of a slot
-                                                              // (the rows land in the next slot / the staging slots; they only feed S rows >= LK)
-    static constexpr int off_scale = off_tail + (128 - LK) * 16;          // float2 (sa, sb) [2][128]: softmax group -> epilogue group
-    static constexpr int off_bar = off_scale + 2 * 128 * 8;
-    static constexpr int kBytes = off_bar + 8 * 54 + 2 * 8 * 16 + 32;
+    static constexpr int off_out = off_ld + kNLd * T::kSlot;  // kNOut staging slots
+    static constexpr int off_zero = off_out + kNOut * T::kSlot;   // zero tile.  (An M=128 MMA reads (128 - LK) rows past the end of
+                                                              // its Q slot: they land in the next slot / the staging slots and only
+                                                              // feed S rows >= LK, which are discarded.)
+    static constexpr int off_bar = off_zero + kZeroBuf;
+    static constexpr int kBytes = off_bar + 8 * 40 + 32;
     static_assert(kBytes <= 232448, "shared memory budget");
 };
 
-enum { B_LD_FULL = 0, B_LD_EMPTY = 6, B_OP_FULL = 12, B_S_FULL = 18, B_S_EMPTY = 19, B_P_FULL = 20,
-       B_P_EMPTY = 22, B_O_FULL = 24, B_O_EMPTY = 26, B_OUT_FULL = 28, B_SC_EMPTY = 31, B_SC_FULL = 33, B_STAGED = 35, B_EARLY = 38,
-       B_FINAL = 46, B_COUNT = 54 };
-
-// Work distribution inside a CTA: the producer thread is the scheduler.  For the item that follows item j-1 it publishes
-//   EARLY[j] when it reaches the slot where the next item's Q/K would be slipped into the ring (kind: 1 = item, 2 = no more
-//            work, 0 = not decided yet -- e.g. only row lines are left and their sample's columns are not complete), and
-//   FINAL[j] the definitive answer (same as EARLY unless that was 0; then after the current item's last chunk).
-// Every role reads these records instead of computing a static schedule.
-struct Rec { int kind, col, b, i; };
-constexpr int kRecRing = 8;      // the producer never runs more than ~3 items ahead of the slowest role
-
-__device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p)
-{
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void wait_done(const unsigned int *cnt, unsigned int need)
-{
-    unsigned int spins = 0;
-    while (ld_acquire(cnt) < need) {
-        __nanosleep(64);
-        if (++spins > (1u << 24)) __trap();
-    }
-}
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+enum { B_LD_FULL = 0, B_LD_EMPTY = 8, B_OP_FULL = 16, B_S_FULL = 24, B_S_EMPTY = 25, B_P_FULL = 26,
+       B_P_EMPTY = 28, B_O_FULL = 30, B_O_EMPTY = 32, B_OUT_FREE = 34, B_STAGED = 36, B_COUNT = 38 };
 
 template <int LK, bool BF>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -151,18 +95,15 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
 {
     using T = Tiles<LK, BF>;
     using S = FwdSmem<LK, BF>;
-    constexpr int TERMS = BF ? 1 : 3;
     constexpr int kNLd = S::kNLd;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S::off_bar);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::off_bar + 8 * B_COUNT + 2 * kRecRing * 16);
-    float2 *scale = reinterpret_cast<float2 *>(smem + S::off_scale);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::off_bar + 8 * B_COUNT);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NCH = p.C / kNC;
     const int KQ = p.Cq / 16;                 // k-steps of the S MMA
-    const int n_items = total_items(p);
-    Rec *rec_early = reinterpret_cast<Rec *>(smem + S::off_bar + 8 * B_COUNT);
-    Rec *rec_final = rec_early + kRecRing;
+    const int nk = p.sp.total > (int)blockIdx.x ? (p.sp.total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    auto item_of = [&](int k) { return decode_item(p.sp, (int)blockIdx.x + k * (int)gridDim.x); };
     // ring order:  Q0 K0 | V0[0..qkpos) Q1 K1 V0[qkpos..NCH) | V1[0..qkpos) Q2 K2 ...   (Q,K of the next item are slipped in
     // after the first chunks of the current one, so neither S(k+1) nor the first P V chunk of an item waits for the other)
     const int qkpos = NCH >= 3 ? 2 : NCH - 1;
@@ -172,45 +113,22 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             mbar_init(&bars[B_LD_FULL + i], 1); mbar_init(&bars[B_LD_EMPTY + i], 1); mbar_init(&bars[B_OP_FULL + i], kConvThreads);
         }
         for (int i = 0; i < kNOB; ++i) { mbar_init(&bars[B_O_FULL + i], 1); mbar_init(&bars[B_O_EMPTY + i], 128); }
-        for (int i = 0; i < kNOut; ++i) { mbar_init(&bars[B_OUT_FULL + i], 1); mbar_init(&bars[B_STAGED + i], 128); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_SC_EMPTY + i], 128); mbar_init(&bars[B_SC_FULL + i], 128); }
-        for (int i = 0; i < kRecRing; ++i) { mbar_init(&bars[B_EARLY + i], 1); mbar_init(&bars[B_FINAL + i], 1); }
+        for (int i = 0; i < kNOut; ++i) { mbar_init(&bars[B_OUT_FREE + i], 1); mbar_init(&bars[B_STAGED + i], 128); }
         mbar_init(&bars[B_S_FULL], 1); mbar_init(&bars[B_S_EMPTY], 128);
         for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_P_FULL + i], 128); mbar_init(&bars[B_P_EMPTY + i], 1); }
         fence_mbar_init();
         prefetch_tmap(&mqc); prefetch_tmap(&mqr); prefetch_tmap(&mkc); prefetch_tmap(&mkr);
         prefetch_tmap(&mvc); prefetch_tmap(&mvr); prefetch_tmap(&moc); prefetch_tmap(&mor);
     }
+    if (tid < kZeroBuf / 16) {                                 // zero tile (read by the async proxy: fence before the barrier)
+        reinterpret_cast<uint4 *>(smem + S::off_zero)[tid] = make_uint4(0, 0, 0, 0);
+        fence_proxy_async();
+    }
     if (warp == 0) tmem_alloc<kTmemCols>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    // Programmatic dependent launch: the row pass is launched while the column pass is still draining; its CTAs load q,k,v,
-    // compute S, the row softmax and the first P V products right away and only wait (pdl_wait) where they first touch what
-    // the column pass produces: the column statistics (softmax group) and the partial output (store warp).
-    pdl_launch_dependents();
-
-    // ---- item records (see Rec): blocking / non-blocking readers used by every role
-    auto rec_item = [&](const Rec &r) { Item it; it.col = r.col; it.b = r.b; it.i = r.i; it.L = r.col ? p.H : p.W; return it; };
-    auto early_kind = [&](int j, Item &it) {                 // blocking on the early decision only
-        mbar_wait(&bars[B_EARLY + (j & (kRecRing - 1))], (j / kRecRing) & 1);
-        const Rec r = rec_early[j & (kRecRing - 1)];
-        if (r.kind == 1) it = rec_item(r);
-        return r.kind;
-    };
-    auto get_item = [&](int j, Item &it) {                   // blocking on the definitive answer; false = no more work
-        mbar_wait(&bars[B_FINAL + (j & (kRecRing - 1))], (j / kRecRing) & 1);
-        const Rec r = rec_final[j & (kRecRing - 1)];
-        if (r.kind == 1) it = rec_item(r);
-        return r.kind == 1;
-    };
-    auto try_item = [&](int j, Item &it) {                   // non-blocking: 1 item, 2 end, -1 not known yet
-        if (!mbar_try_wait(&bars[B_FINAL + (j & (kRecRing - 1))], (j / kRecRing) & 1)) return -1;
-        const Rec r = rec_final[j & (kRecRing - 1)];
-        if (r.kind == 1) it = rec_item(r);
-        return r.kind;
-    };
 
     if (warp >= kWarpProducer) {
         reg_dec<kRegsMisc>();
@@ -219,94 +137,34 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             if (lane == 0) {
                 uint32_t g = 0;
                 int dbg_n = 0;
-                const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
-                auto emit = [&](const CUtensorMap *mc, const CUtensorMap *mr, int c0, const Item &it) {
+                (void)dbg_n;
+                auto emit = [&](const CUtensorMap *mc, const CUtensorMap *mr, int c0, const Item &it, int start) {
                     const CUtensorMap *m = it.col ? mc : mr;
-                    const uint64_t pol = it.col && it.b >= p.keep_from ? pol_keep : pol_stream;
-                    const int cw = it.col ? it.i : 0, ch = it.col ? 0 : it.i;
+                    const int cw = it.col ? it.line : start, ch = it.col ? start : it.line;
                     const int slot = g % kNLd;
                     mbar_wait(&bars[B_LD_EMPTY + slot], ((g / kNLd) & 1) ^ 1);
                     CCA_STAMP(0);
                     uint8_t *dst = smem + S::off_ld + slot * T::kSlot;
                     mbar_expect_tx(&bars[B_LD_FULL + slot], T::kSlot);
-                    if (p.hints) {
-                        tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, it.b, pol);
-                        if constexpr (!BF) tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, it.b, pol);
-                    } else {
-                        tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, it.b);
-                        if constexpr (!BF) tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, it.b);
-                    }
+                    tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, it.b);
+                    if constexpr (!BF) tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, it.b);
                     ++g;
                 };
-                // ---- scheduler: hand out the next line of this CTA
-                int static_k = 0;
-                auto try_fetch = [&](Item &it) -> int {            // 1 item, 2 no more work, 0 nothing available right now
-                    if (p.mode != MODE_DYNAMIC) {
-                        const int idx = (int)blockIdx.x + static_k * (int)gridDim.x;
-                        if (idx >= n_items) return 2;
-                        it = decode_item(p, idx);
-                        ++static_k;
-                        return 1;
-                    }
-                    // dynamic: row lines first (in sample order, only of samples whose column lines are all published),
-                    // else the next column line.  All claims are atomicAdd on per-queue counters: no CAS retry storms.
-                    const unsigned total_cols = (unsigned)(p.B * p.W);
-                    unsigned b = ld_acquire(p.sched + 1);             // first sample that may still have row lines to hand out
-                    bool rows_left = false;
-                    for (; b < (unsigned)p.B; ++b) {
-                        if (ld_acquire(p.done + b) < (unsigned)p.W) { rows_left = true; break; }   // not ready yet (keep sample order)
-                        const unsigned r = atomicAdd(p.rown + b, 1u);
-                        if (r < (unsigned)p.H) { it.col = 0; it.b = (int)b; it.i = (int)r; it.L = p.W; return 1; }
-                        atomicMax(p.sched + 1, b + 1);                // this sample's rows are all handed out
-                    }
-                    if (ld_acquire(p.sched + 0) < total_cols) {
-                        const unsigned c = atomicAdd(p.sched + 0, 1u);
-                        if (c < total_cols) {
-                            it.col = 1; it.b = (int)(c / (unsigned)p.W); it.i = (int)(c - it.b * p.W); it.L = p.H;
-                            return 1;
-                        }
-                    }
-                    return rows_left ? 0 : 2;                          // 0: only row lines are left and they are not ready yet
-                };
-                auto fetch_blocking = [&](Item &it) -> int {
-                    unsigned spins = 0;
-                    for (;;) {
-                        const int kd = try_fetch(it);
-                        if (kd) return kd;
-                        __nanosleep(256);
-                        if (++spins > (1u << 22)) __trap();
-                    }
-                };
-                auto publish = [&](int base, Rec *arr, int j, int kind, const Item &it) {
-                    Rec r; r.kind = kind; r.col = it.col; r.b = it.b; r.i = it.i;
-                    arr[j & (kRecRing - 1)] = r;
-                    mbar_arrive(&bars[base + (j & (kRecRing - 1))]);       // release: the record is visible to the waiters
-                };
-                Item cur;
-                cur.col = cur.b = cur.i = cur.L = 0;
-                int kind = fetch_blocking(cur);
-                publish(B_EARLY, rec_early, 0, kind, cur);
-                publish(B_FINAL, rec_final, 0, kind, cur);
-                if (kind == 1) { emit(&mqc, &mqr, 0, cur); emit(&mkc, &mkr, 0, cur); }
-                for (int k = 0; kind == 1; ++k) {
-                    Item nxt = cur;
-                    int nkind = -1;                                 // -1: not decided yet
+                if (nk > 0) {
+                    const Item it0 = item_of(0);
+                    emit(&mqc, &mqr, 0, it0, it0.q0);
+                    emit(&mkc, &mkr, 0, it0, it0.k0);
+                }
+                for (int k = 0; k < nk; ++k) {
+                    const Item it = item_of(k);
                     for (int n = 0; n < NCH; ++n) {
-                        if (n == qkpos) {
-                            nkind = try_fetch(nxt);
-                            publish(B_EARLY, rec_early, k + 1, nkind, nxt);
-                            if (nkind != 0) publish(B_FINAL, rec_final, k + 1, nkind, nxt);
-                            if (nkind == 1) { emit(&mqc, &mqr, 0, nxt); emit(&mkc, &mkr, 0, nxt); }
+                        if (n == qkpos && k + 1 < nk) {
+                            const Item nx = item_of(k + 1);
+                            emit(&mqc, &mqr, 0, nx, nx.q0);
+                            emit(&mkc, &mkr, 0, nx, nx.k0);
                         }
-                        emit(&mvc, &mvr, n * kNC, cur);
+                        emit(&mvc, &mvr, n * kNC, it, it.k0);
                     }
-                    if (nkind == 0) {                               // decided late: after the last chunk of the current item
-                        nkind = fetch_blocking(nxt);
-                        publish(B_FINAL, rec_final, k + 1, nkind, nxt);
-                        if (nkind == 1) { emit(&mqc, &mqr, 0, nxt); emit(&mkc, &mkr, 0, nxt); }
-                    }
-                    kind = nkind;
-                    cur = nxt;
                 }
             }
         } else if (warp == kWarpMma) {
@@ -315,17 +173,12 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             const uint32_t idesc_o = instr_desc(kFmtBF16, kFmtBF16, 128, kNC, false, true);
             uint32_t u = 0, oc = 0;
             int dbg_n = lane == 0 ? 0 : 512;
-            // operand of ring item u = load slot u % kNLd: fp32 -> bf16 hi/lo planes written in place by the converters;
-            //                                              bf16 -> the TMA tile itself, read with SWIZZLE_128B descriptors
+            (void)dbg_n;
             const uint32_t ld_base = smem_u32(smem + S::off_ld);
-            auto wait_item = [&](uint32_t g) {
-                mbar_wait(&bars[(BF ? B_LD_FULL : B_OP_FULL) + g % kNLd], (g / kNLd) & 1);
-            };
-            auto free_item = [&](uint32_t g) {
-                commit_to(&bars[B_LD_EMPTY + g % kNLd]);
-            };
+            auto wait_item = [&](uint32_t g) { mbar_wait(&bars[(BF ? B_LD_FULL : B_OP_FULL) + g % kNLd], (g / kNLd) & 1); };
+            auto free_item = [&](uint32_t g) { commit_to(&bars[B_LD_EMPTY + g % kNLd]); };
             auto item_addr = [&](uint32_t g) { return ld_base + (g % kNLd) * T::kSlot; };
-            auto issue_s = [&](int k) {            // S(k) = Q K^T from items u (Q) and u+1 (K)
+            auto issue_s = [&](int k) {            // S(k) = Q K^T from ring items u (Q) and u+1 (K)
                 const uint32_t qb = item_addr(u), kb = item_addr(u + 1);
                 wait_item(u); wait_item(u + 1);
                 mbar_wait(&bars[B_S_EMPTY], (k & 1) ^ 1);
@@ -346,21 +199,15 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                 free_item(u); free_item(u + 1);
                 u += 2;
             };
-            Item it_unused;
-            bool have = get_item(0, it_unused);
-            if (have) issue_s(0);
-            for (int k = 0; have; ++k) {
-                int nkind = -1;
+            if (nk > 0) issue_s(0);
+            for (int k = 0; k < nk; ++k) {
                 CCA_STAMP(2);
                 mbar_wait(&bars[B_P_FULL + (k & 1)], (k >> 1) & 1);
                 tc_fence_after();
                 CCA_STAMP(2);
                 const uint32_t pbuf = tmem + kTmemP + (k & 1) * 128;
                 for (int n = 0; n < NCH; ++n, ++u, ++oc) {
-                    if (n == qkpos) {                              // same decision the producer took when it filled the ring
-                        nkind = early_kind(k + 1, it_unused);
-                        if (nkind == 1) issue_s(k + 1);
-                    }
+                    if (n == qkpos && k + 1 < nk) issue_s(k + 1);
                     const uint32_t vb = item_addr(u);
                     const uint32_t ob = oc % kNOB;
                     wait_item(u);
@@ -389,111 +236,51 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                     CCA_STAMP(2);
                 }
                 commit_to(&bars[B_P_EMPTY + (k & 1)]);
-                if (nkind == 0) {                                  // late decision: Q,K of the next item follow the last chunk
-                    have = get_item(k + 1, it_unused);
-                    if (have) issue_s(k + 1);
-                } else have = nkind == 1;
             }
         } else if (warp == kWarpStore) {
-            // =============================== store warp (one lane): staging slots <-> global ===============================
-            // Per output chunk c (slot c % kNOut): make the slot ready for the epilogue group (a row item gets its column
-            // partial prefetched by TMA, two chunks ahead), and once the group has staged the merged tile, TMA-store it.
-            // Column items are published (per-sample counter) after their last store has completed.
+            // =============================== store warp (one lane) ===============================
             if (lane == 0) {
-                uint32_t prep = 0;                         // chunks prepared so far (chunk c belongs to item c / NCH)
-                const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
-                int pub_k = 0;                             // items [0, pub_k) are published / need no publishing
-                // a row chunk must not wait for a column item this warp has yet to publish (static fused order only:
-                // the dynamic scheduler hands out a row line only after all column lines of its sample were published)
-                auto can_prepare = [&](uint32_t c) {
-                    Item nx;
-                    if (try_item((int)(c / NCH), nx) != 1) return false;
-                    if (nx.col || p.mode != MODE_FUSED) return true;
-                    for (int j = pub_k; j < (int)(c / NCH); ++j) {
-                        Item pj;
-                        if (try_item(j, pj) == 1 && pj.col && pj.b == nx.b) return false;
-                    }
-                    return true;
-                };
-                auto prepare = [&](uint32_t c, const Item &it) {
-                    const int n = c % NCH, os = c % kNOut;
-                    if (it.col) { mbar_arrive(&bars[B_OUT_FULL + os]); return; }
-                    if (p.mode <= MODE_DYNAMIC || p.sync) { wait_done(p.done + it.b, (unsigned)p.W); fence_proxy_async_all(); }
-                    else pdl_wait();                           // (row pass launched ahead of the column pass's completion)
-                    uint8_t *dst = smem + S::off_out + os * T::kSlot;
-                    mbar_expect_tx(&bars[B_OUT_FULL + os], T::kSlot);
-                    if (p.hints) {                                 // the partial is read exactly once
-                        tma_load_4d(dst, &mor, &bars[B_OUT_FULL + os], n * kNC, 0, it.i, it.b, pol_stream);
-                        if constexpr (!BF) tma_load_4d(dst + T::kTile, &mor, &bars[B_OUT_FULL + os], n * kNC + 32, 0, it.i, it.b, pol_stream);
-                    } else {
-                        tma_load_4d(dst, &mor, &bars[B_OUT_FULL + os], n * kNC, 0, it.i, it.b);
-                        if constexpr (!BF) tma_load_4d(dst + T::kTile, &mor, &bars[B_OUT_FULL + os], n * kNC + 32, 0, it.i, it.b);
-                    }
-                };
-                Item it, prev;
-                bool has_prev = false;
-                prev.col = prev.b = prev.i = prev.L = 0;
-                for (int k = 0; get_item(k, it); ++k) {
+                pdl_wait();                                // statistics kernel complete: counters and the head of `out` are cleared
+                int pending = -1;                          // sample whose zero share this lane has issued but not yet published
+                for (int k = 0; k < nk; ++k) {
+                    const Item it = item_of(k);
                     const CUtensorMap *mo = it.col ? &moc : &mor;
-                    const int cw = it.col ? it.i : 0, ch = it.col ? 0 : it.i;
+                    const int cw = it.col ? it.line : it.q0, ch = it.col ? it.q0 : it.line;
+                    const int zb = it.b + p.ahead;
+                    if (zb < p.sp.B) {                     // zero-ahead: this item's share of sample zb
+                        const long lo = (long)it.j * p.share;
+                        const long hi = lo + p.share < p.sample_bytes ? lo + p.share : p.sample_bytes;
+                        uint8_t *dst = p.out + (long)zb * p.sample_bytes;
+                        for (long o = lo; o < hi; o += kZeroBuf)
+                            bulk_store(dst + o, smem + S::off_zero, (uint32_t)(hi - o < kZeroBuf ? hi - o : kZeroBuf));
+                        tma_store_commit();
+                        pending = zb;
+                    }
                     for (int n = 0; n < NCH; ++n) {
                         const uint32_t c = (uint32_t)k * NCH + n;
                         const int os = c % kNOut;
-                        while (prep <= c) {                        // not prefetched: prepare the current chunk now
-                            tma_store_wait_read<1>();
-                            Item pi = it;
-                            if ((int)(prep / NCH) != k) get_item((int)(prep / NCH), pi);
-                            prepare(prep, pi);
-                            ++prep;
-                        }
                         mbar_wait(&bars[B_STAGED + os], (c / kNOut) & 1);
-                        const uint8_t *slot = smem + S::off_out + os * T::kSlot;
-                        if (p.hints) {
-                            const uint64_t pol = it.col && it.b >= p.keep_from ? pol_keep : pol_stream;
-                            tma_store_4d(mo, slot, n * kNC, cw, ch, it.b, pol);
-                            if constexpr (!BF) tma_store_4d(mo, slot + T::kTile, n * kNC + 32, cw, ch, it.b, pol);
-                        } else {
-                            tma_store_4d(mo, slot, n * kNC, cw, ch, it.b);
-                            if constexpr (!BF) tma_store_4d(mo, slot + T::kTile, n * kNC + 32, cw, ch, it.b);
-                        }
-                        tma_store_commit();
-                        if (p.sync && n == 0 && has_prev && prev.col) {
-                            // publish the previous column line: its last store was committed a chunk period ago
-                            tma_store_wait_all<1>();
-                            fence_proxy_async_all();
-                            __threadfence();
-                            atomicAdd(p.done + prev.b, 1u);
-                        }
-                        if (n == NCH - 1) { prev = it; has_prev = true; }
-                        if (n == NCH - 1) {
-                            if (it.col && p.mode <= MODE_DYNAMIC) {
-                                // publish this column line: its stores (async proxy) and the stats written by the softmax group
+                        if (n == 0) {
+                            if (pending >= 0) {            // the zero copies were issued a whole item-prologue ago: this wait is short
                                 tma_store_wait_all<0>();
-                                fence_proxy_async_all();
-                                __threadfence();
-                                atomicAdd(p.done + it.b, 1u);
+                                publish_count(p.zdone + pending);
+                                pending = -1;
                             }
-                            pub_k = k + 1;
+                            if (it.b >= p.ahead) {         // every share of this sample's output has been cleared
+                                wait_count(p.zdone + it.b, (unsigned)p.sp.per_sample);
+                                fence_proxy_async_all();
+                            }
                         }
-                        // keep the ring of kNOut slots full: chunk c+kNOut reuses the slot of the store just issued, as soon as
-                        // that store has been read out of shared memory (a few hundred cycles; this lane has nothing else to do
-                        // until the next chunk is staged).  The partial of a row item is thus in flight two full chunk periods
-                        // before the epilogue needs it -- one period did not cover the L2 latency of the tile.
-                        while (prep <= c + kNOut && can_prepare(prep)) {
-                            Item pi;
-                            try_item((int)(prep / NCH), pi);
-                            if (prep == c + kNOut) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
-                            prepare(prep, pi);
-                            ++prep;
-                        }
+                        const uint8_t *slot = smem + S::off_out + os * T::kSlot;
+                        tma_reduce_add_4d(mo, slot, n * kNC, cw, ch, it.b);
+                        if constexpr (!BF) tma_reduce_add_4d(mo, slot + T::kTile, n * kNC + 32, cw, ch, it.b);
+                        tma_store_commit();
+                        tma_store_wait_read<0>();          // the tile has been read out of shared memory: hand the slot back
+                        mbar_arrive(&bars[B_OUT_FREE + os]);
                     }
                 }
                 tma_store_wait_all<0>();
-                if (p.sync && has_prev && prev.col) {         // the last column line of this CTA
-                    fence_proxy_async_all();
-                    __threadfence();
-                    atomicAdd(p.done + prev.b, 1u);
-                }
+                if (pending >= 0) publish_count(p.zdone + pending);
             }
         }
     } else if (warp >= kWarpConv0) {
@@ -501,6 +288,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
         reg_dec<kRegsConvF>();
         const int t = tid - kWarpConv0 * 32;
         int dbg_n = t == 0 ? 0 : 512;
+        (void)dbg_n;
         uint32_t g = 0;
         auto convert_next = [&](int count) {                       // the next `count` ring slots, whatever they hold
             for (int e = 0; e < count; ++e, ++g) {
@@ -514,23 +302,12 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             }
         };
         if constexpr (!BF) {                                       // bf16 tiles need no conversion
-            Item it;
-            bool have = get_item(0, it);
-            if (have) convert_next(2);                             // Q, K of the first item
-            for (int k = 0; have; ++k) {                           // mirrors the ring order chosen by the producer
-                int nkind = -1;
+            if (nk > 0) convert_next(2);                           // Q, K of the first item
+            for (int k = 0; k < nk; ++k)                           // mirrors the ring order of the producer
                 for (int n = 0; n < NCH; ++n) {
-                    if (n == qkpos) {
-                        nkind = early_kind(k + 1, it);
-                        if (nkind == 1) convert_next(2);
-                    }
+                    if (n == qkpos && k + 1 < nk) convert_next(2);
                     convert_next(1);
                 }
-                if (nkind == 0) {
-                    have = get_item(k + 1, it);
-                    if (have) convert_next(2);
-                } else have = nkind == 1;
-            }
         }
     } else if (warp >= 4) {
         // =============================== softmax group (128 threads, TMEM lane == query pixel) ===============================
@@ -538,36 +315,30 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
         const int r = tid - 128;
         const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         int dbg_n = r == 0 ? 0 : 512;
-        Item it;
-        for (int k = 0; get_item(k, it); ++k) {
-            const bool rvalid = r < it.L;
+        (void)dbg_n;
+        pdl_wait();                                                // parts come from the statistics kernel
+        for (int k = 0; k < nk; ++k) {
+            const Item it = item_of(k);
+            const bool rvalid = r < it.lq;
+            // final log2-sum-exp2 of this query pixel from the per-(direction, key block) planes
+            float lse2 = 0.f;
+            if (rvalid) {
+                const long pix = item_pixel(p.sp, it, r);
+                float m = -INFINITY;
+                for (int i = 0; i < p.sp.nparts; ++i) m = fmaxf(m, __ldcg(p.parts + (long)i * p.npix + pix));
+                float s = 0.f;
+                for (int i = 0; i < p.sp.nparts; ++i) s += exp2f(__ldcg(p.parts + (long)i * p.npix + pix) - m);
+                lse2 = m + log2f(s);
+                if (!it.col && it.ik == 0) p.lse[pix] = lse2 * kLn2;
+            }
+            const int self = it.col ? it.q0 + r - it.k0 : -1;          // masked key of this query (column branch only)
             CCA_STAMP(3);
             mbar_wait(&bars[B_S_FULL], k & 1);
-            tc_fence_after();
-            CCA_STAMP(3);
-            // two streaming passes over the S row in TMEM, 16 columns at a time (small loops instead of a 112-element
-            // register array: the instruction footprint matters -- the unrolled version cost ~16K cycles on its first run)
-            // ---- pass 1: row max of the valid, unmasked logits (log2 units)
-            float m = -INFINITY;
-#pragma unroll 1
-            for (int c0 = 0; c0 < LK; c0 += 16) {
-                float s[16];
-                tmem_ld16(tl + c0, reinterpret_cast<uint32_t *>(s));
-                tmem_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const int j = c0 + e;
-                    const bool ok = j < it.L && !(it.col && j == r);
-                    m = fmaxf(m, ok ? s[e] * kLog2e : -INFINITY);
-                }
-            }
-            const float msub = (m == -INFINITY) ? 0.f : m;      // fully masked row (L == 1 in a column item)
-            // ---- pass 2: P = exp2(s - m) -> TMEM as packed bf16 pairs (hi at [pdst, +LK/2), lo at [pdst+LK/2, +LK/2)), row sum
-            CCA_STAMP(3);
             mbar_wait(&bars[B_P_EMPTY + (k & 1)], ((k >> 1) & 1) ^ 1);    // P V of item k-2 has finished reading this buffer
             tc_fence_after();
+            CCA_STAMP(3);
+            // P = exp2(s log2e - lse2) -> TMEM as packed bf16 pairs (hi at [pdst, +LK/2), lo at [pdst+LK/2, +LK/2))
             const uint32_t pdst = tl + kTmemP + (k & 1) * 128;
-            float l = 0.f;
 #pragma unroll 1
             for (int c0 = 0; c0 < LK; c0 += 16) {
                 float s[16];
@@ -577,11 +348,10 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const int j = c0 + 2 * e;
-                    const bool ok0 = rvalid && j < it.L && !(it.col && j == r);
-                    const bool ok1 = rvalid && j + 1 < it.L && !(it.col && j + 1 == r);
-                    const float p0 = ok0 ? exp2f(s[2 * e] * kLog2e - msub) : 0.f;
-                    const float p1 = ok1 ? exp2f(s[2 * e + 1] * kLog2e - msub) : 0.f;
-                    l += p0 + p1;
+                    const bool ok0 = rvalid && j < it.lk && j != self;
+                    const bool ok1 = rvalid && j + 1 < it.lk && j + 1 != self;
+                    const float p0 = ok0 ? exp2f(s[2 * e] * kLog2e - lse2) : 0.f;
+                    const float p1 = ok1 ? exp2f(s[2 * e + 1] * kLog2e - lse2) : 0.f;
                     if constexpr (BF) hi[e] = pack_bf16(p0, p1);
                     else split2(p0, p1, hi[e], lo[e]);
                 }
@@ -593,29 +363,6 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             mbar_arrive(&bars[B_P_FULL + (k & 1)]);
             mbar_arrive(&bars[B_S_EMPTY]);
             CCA_STAMP(3);
-            // ---- per-pixel statistics / merge scales (off the MMA's critical path now)
-            float sa = 0.f, sb = 0.f;
-            if (!it.col && (p.mode <= MODE_DYNAMIC || p.sync)) wait_done(p.done + it.b, (unsigned)p.W);   // column stats of this sample complete
-            else if (!it.col) pdl_wait();                      // row pass launched ahead of the column pass's completion
-            if (rvalid) {
-                const long pix = it.col ? ((long)it.b * p.H + r) * p.W + it.i : ((long)it.b * p.H + it.i) * p.W + r;
-                const float mn = m * kLn2;                       // natural-log units
-                if (it.col) {
-                    p.stats[pix] = make_float2(mn, l);
-                    sa = l > 0.f ? 1.f / l : 0.f;
-                } else {
-                    const float2 pc = __ldcg(p.stats + pix);
-                    const float mm = fmaxf(mn, pc.x);
-                    const float ar = exp2f((mn - mm) * kLog2e);
-                    const float ac = pc.y > 0.f ? exp2f((pc.x - mm) * kLog2e) : 0.f;
-                    const float lt = ar * l + ac * pc.y;
-                    sa = ar / lt; sb = ac * pc.y / lt;
-                    p.lse[pix] = mm + logf(lt);
-                }
-            }
-            mbar_wait(&bars[B_SC_EMPTY + (k & 1)], ((k >> 1) & 1) ^ 1);   // epilogue has consumed the scales of item k-2
-            scale[(k & 1) * 128 + r] = make_float2(sa, sb);
-            mbar_arrive(&bars[B_SC_FULL + (k & 1)]);          // release: scales and the stats / lse written above
         }
     } else {
         // =============================== epilogue group (128 threads, TMEM lane == query pixel) ===============================
@@ -624,79 +371,40 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
         const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
         uint32_t oc = 0;
         int dbg_n = tid == 0 ? 0 : 512;
-        Item it;
-        for (int k = 0; get_item(k, it); ++k) {
-            float sa = 0.f, sb = 0.f;
+        (void)dbg_n;
+        for (int k = 0; k < nk; ++k) {
             for (int n = 0; n < NCH; ++n, ++oc) {
                 const int os = oc % kNOut;
                 const uint32_t ob = oc % kNOB;
                 uint8_t *slot = smem + S::off_out + os * T::kSlot;
                 CCA_STAMP(4);
-                mbar_wait(&bars[B_OUT_FULL + os], (oc / kNOut) & 1);     // slot free (column item) / column partial landed (row item)
-                CCA_STAMP(4);
+                mbar_wait(&bars[B_OUT_FREE + os], ((oc / kNOut) & 1) ^ 1);   // the store of chunk oc - kNOut has left the slot
                 mbar_wait(&bars[B_O_FULL + ob], (oc / kNOB) & 1);
                 tc_fence_after();
                 CCA_STAMP(4);
-                if (n == 0) {
-                    mbar_wait(&bars[B_SC_FULL + (k & 1)], (k >> 1) & 1);
-                    const float2 sc = scale[(k & 1) * 128 + r];
-                    sa = sc.x; sb = sc.y;
-                    mbar_arrive(&bars[B_SC_EMPTY + (k & 1)]);
-                }
                 float o[kNC];
 #pragma unroll
                 for (int c0 = 0; c0 < kNC; c0 += 16) tmem_ld16(tl + kTmemO + ob * kNC + c0, reinterpret_cast<uint32_t *>(o + c0));
                 tmem_ld_wait();
-                CCA_STAMP(4);
                 tc_fence_before();
                 mbar_arrive(&bars[B_O_EMPTY + ob]);
-                if (r < it.L) {                                          // rows >= L are clipped by the TMA store
+                // rows >= lq are exact zeros (their P row is zero): inside the image they add nothing, outside the TMA clips them
+                if (r < LK) {
                     uint8_t *row = slot + r * 128;
                     const int sw = r & 7;
                     if constexpr (BF) {
-                        // bf16 staging tile: one 128-byte row = 64 channels = 8 chunks of 8 bf16
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            uint4 *dst = reinterpret_cast<uint4 *>(row + ((j ^ sw) * 16));
-                            float v[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) v[e] = o[8 * j + e] * sa;
-                            if (!it.col) {
-                                const uint4 q = *dst;
-                                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    v[2 * e] = fmaf(bf_lo(w[e]), sb, v[2 * e]);
-                                    v[2 * e + 1] = fmaf(bf_hi(w[e]), sb, v[2 * e + 1]);
-                                }
-                            }
-                            *dst = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                        }
-                    } else if (it.col) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {                   // 16 chunks of 4 channels
-                            float4 *dst = reinterpret_cast<float4 *>(row + (j >> 3) * T::kTile + (((j & 7) ^ sw) * 16));
-                            *dst = make_float4(o[4 * j] * sa, o[4 * j + 1] * sa, o[4 * j + 2] * sa, o[4 * j + 3] * sa);
-                        }
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<uint4 *>(row + ((j ^ sw) * 16)) =
+                                make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]),
+                                           pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
                     } else {
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {                    // two batches of 8: all loads of a batch before its stores
-                            float4 q[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                q[j] = *reinterpret_cast<const float4 *>(row + h * T::kTile + ((j ^ sw) * 16));
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const int e = 32 * h + 4 * j;
-                                float4 v;
-                                v.x = fmaf(q[j].x, sb, o[e] * sa);         v.y = fmaf(q[j].y, sb, o[e + 1] * sa);
-                                v.z = fmaf(q[j].z, sb, o[e + 2] * sa);     v.w = fmaf(q[j].w, sb, o[e + 3] * sa);
-                                *reinterpret_cast<float4 *>(row + h * T::kTile + ((j ^ sw) * 16)) = v;
-                            }
-                        }
+                        for (int j = 0; j < 16; ++j)
+                            *reinterpret_cast<float4 *>(row + (j >> 3) * T::kTile + (((j & 7) ^ sw) * 16)) =
+                                make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
                     }
                 }
-                CCA_STAMP(4);
                 fence_proxy_async();
                 mbar_arrive(&bars[B_STAGED + os]);                       // the store warp takes over
                 CCA_STAMP(4);
@@ -708,105 +416,85 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
     if (warp == 0) tmem_dealloc<kTmemCols>(tmem);
 }
 
-long long *g_dbg = nullptr;   // set through cca_b200__set_debug_buffer (profiling aid, not part of the ABI)
+long long *g_dbg = nullptr;   // timeline buffer (tools/tc_timeline.py, -DCCA_TIMELINE builds)
 
 template <int LK, bool BF>
-cudaError_t launch_fwd(const void *q, const void *k, const void *v, void *out, float *lse, float2 *stats, unsigned int *cnt,
-                       Dims d, int mode, cudaStream_t st, const char **why)
+cudaError_t launch_fwd(const void *q, const void *k, const void *v, void *out, float *lse, const float *parts, unsigned int *zdone,
+                       Dims d, int ahead, cudaStream_t st, const char **why)
 {
     CUtensorMap m[8];
     const void *base[4] = {q, k, v, out};
     const int ch[4] = {d.Cq, d.Cq, d.C, d.C};
     for (int t = 0; t < 4; ++t)
         for (int r = 0; r < 2; ++r)
-            if (!make_map(&m[2 * t + r], base[t], d.B, d.H, d.W, ch[t], LK, r == 0, BF)) {
+            if (!get_map(&m[2 * t + r], base[t], d.B, d.H, d.W, ch[t], LK, r == 0, BF)) {
                 if (why) *why = "cuTensorMapEncodeTiled failed";
                 return cudaErrorInvalidValue;
             }
     FwdParams p;
-    p.B = d.B; p.H = d.H; p.W = d.W; p.C = d.C; p.Cq = d.Cq;
-    p.mode = mode; p.stats = stats; p.lse = lse; p.sched = cnt; p.done = cnt + 2; p.rown = cnt + 2 + d.B;
-    p.dbg = g_dbg ? g_dbg + (mode == MODE_ROW_ONLY ? 2560 : 0) : nullptr;
-    // L2 residency: keep (evict_last) what the column pass touches for its last samples -- as many as fit the budget --
-    // because the row pass starts with exactly those; everything else is marked evict_first
-    const double per_sample = (2.0 * d.Cq + 2.0 * d.C) * d.H * d.W * (BF ? 2 : 4);
-    int keep = (int)(tc_l2_keep_mb() * 1e6 / per_sample);
-    if (keep > d.B) keep = d.B;
-    p.hints = tc_l2_hints();
-    p.keep_from = mode <= MODE_DYNAMIC ? 0 : d.B - keep;
-    p.sync = (mode == MODE_COL_ONLY || mode == MODE_ROW_ONLY) && tc_pdl() == 2 ? 1 : 0;
+    p.sp = make_space(d.B, d.H, d.W);
+    p.C = d.C; p.Cq = d.Cq;
+    p.npix = (long)d.B * d.H * d.W;
+    p.parts = parts; p.lse = lse; p.zdone = zdone;
+    p.out = reinterpret_cast<uint8_t *>(out);
+    p.sample_bytes = (long)d.H * d.W * d.C * (BF ? 2 : 4);
+    p.share = zero_share_bytes(p.sample_bytes, p.sp.per_sample);
+    p.ahead = ahead;
+    p.dbg = g_dbg;
     auto kern = cca_tc_fwd_kernel<LK, BF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem<LK, BF>::kBytes);
     if (e != cudaSuccess) return e;
-    const int items = mode <= MODE_DYNAMIC ? d.B * (d.W + d.H) : (mode == MODE_COL_ONLY ? d.B * d.W : d.B * d.H);
-    const int grid = items < sm_count() ? items : sm_count();
+    const int sms = sm_count();
+    const int grid = p.sp.total < sms ? p.sp.total : sms;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = FwdSmem<LK, BF>::kBytes; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = (mode == MODE_ROW_ONLY && tc_pdl()) ? 1 : 0;     // only the row pass may start ahead of its predecessor
+    cfg.numAttrs = tc_pdl() ? 1 : 0;     // may start ahead of the statistics kernel's completion (griddepcontrol.wait inside)
     e = cudaLaunchKernelEx(&cfg, kern, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], p);
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-// Launch policy of the forward (CCA_B200_FUSED): 0 = two launches (column pass, row pass); 1 = ONE launch with dynamic
-// scheduling (lines are claimed from a column queue and a row queue; a row line only once the column lines of its sample
-// are complete, so the partial output and q,k,v are re-read from L2 and no CTA ever waits on another); 2 = one launch with
-// the static interleaved order (kept for comparison: it stalls on the column->row dependency).
-int g_fused = -1;
-int fused_mode()
-{
-    if (g_fused < 0) {
-        const char *e = getenv("CCA_B200_FUSED");
-        g_fused = e ? atoi(e) : 0;
-        if (g_fused < 0 || g_fused > 2) g_fused = 0;
-    }
-    return g_fused;
-}
-
 }  // namespace
 
 void set_tc_debug_buffer(void *p) { g_dbg = reinterpret_cast<long long *>(p); }
-void set_tc_two_pass(int on) { g_fused = on == 1 ? 0 : (on == 0 ? 1 : 2); }   // 1: two launches, 0: dynamic fused, 2: static fused
 
 bool tc_forward_supported(Dims d, int dtype) { return tc::shape_supported(d, dtype); }
 
-// q,k,v,out are channels-last (NHWC), fp32 or bf16.  ws: [B*H*W] float2 stats, then [B] unsigned counters.
-namespace {
-template <bool BF>
-cudaError_t launch_fwd_lk(int lk, const void *q, const void *k, const void *v, void *out, float *lse, float2 *stats,
-                          unsigned int *cnt, Dims d, int mode, cudaStream_t st, const char **why)
+// Workspace of the forward: [nparts][B*H*W] fp32 partial lse planes, then [B] unsigned zero-ahead counters.
+size_t tc_forward_workspace(Dims d)
 {
-    return lk == 80 ? launch_fwd<80, BF>(q, k, v, out, lse, stats, cnt, d, mode, st, why)
-                    : launch_fwd<112, BF>(q, k, v, out, lse, stats, cnt, d, mode, st, why);
+    const ItemSpace sp = make_space(d.B, d.H, d.W);
+    const size_t parts = (size_t)sp.nparts * d.B * d.H * d.W * sizeof(float);
+    return ((parts + 15) & ~(size_t)15) + (((size_t)d.B * sizeof(unsigned int) + 15) & ~(size_t)15);
 }
-}  // namespace
 
+// q,k,v,out are channels-last (NHWC), fp32 or bf16.  Two launches: statistics pre-pass (q,k only), values.
 cudaError_t tc_forward(const void *q, const void *k, const void *v, void *out, float *lse, void *ws, Dims d, int dtype,
                        cudaStream_t st, const char **why)
 {
-    float2 *stats = reinterpret_cast<float2 *>(ws);
-    unsigned int *cnt = reinterpret_cast<unsigned int *>(stats + (size_t)d.B * d.H * d.W);   // [2] queue heads, [B] columns done, [B] rows handed out
-    const int lkc = lk_for(d.H), lkr = lk_for(d.W);
+    const ItemSpace sp = make_space(d.B, d.H, d.W);
+    const long npix = (long)d.B * d.H * d.W;
+    float *parts = reinterpret_cast<float *>(ws);
+    const size_t parts_bytes = ((size_t)sp.nparts * npix * sizeof(float) + 15) & ~(size_t)15;
+    unsigned int *zdone = reinterpret_cast<unsigned int *>(reinterpret_cast<uint8_t *>(ws) + parts_bytes);
     const bool bf = dtype == CCA_BF16;
-    auto go = [&](int lk, int mode) {
-        return bf ? launch_fwd_lk<true>(lk, q, k, v, out, lse, stats, cnt, d, mode, st, why)
-                  : launch_fwd_lk<false>(lk, q, k, v, out, lse, stats, cnt, d, mode, st, why);
-    };
-    if (lkc == lkr && fused_mode() != 0) {
-        cudaError_t e = cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * (2 * d.B + 2), st);
-        if (e != cudaSuccess) return e;
-        return go(lkc, fused_mode() == 1 ? MODE_DYNAMIC : MODE_FUSED);
-    }
-    cudaError_t e = cudaSuccess;
-    if (tc_pdl() == 2) e = cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * (2 * d.B + 2), st);   // done[] of the overlapped row pass
+    const long sample_bytes = (long)d.H * d.W * d.C * (bf ? 2 : 4);
+    int ahead = tc_zero_ahead();
+    if (ahead < 1) ahead = 1;
+    const int head = ahead < d.B ? ahead : d.B;
+    // statistics + clear the first `ahead` samples of out and the counters
+    cudaError_t e = tc_stats(q, k, parts, out, (long)head * sample_bytes, zdone, d.B, d, dtype, st, why);
     if (e != cudaSuccess) return e;
-    e = go(lkc, MODE_COL_ONLY);
-    if (e != cudaSuccess) return e;
-    return go(lkr, MODE_ROW_ONLY);
+    const int lk = lk_for(max_tile(sp));
+    if (bf)
+        return lk == 80 ? launch_fwd<80, true>(q, k, v, out, lse, parts, zdone, d, ahead, st, why)
+                        : launch_fwd<112, true>(q, k, v, out, lse, parts, zdone, d, ahead, st, why);
+    return lk == 80 ? launch_fwd<80, false>(q, k, v, out, lse, parts, zdone, d, ahead, st, why)
+                    : launch_fwd<112, false>(q, k, v, out, lse, parts, zdone, d, ahead, st, why);
 }
 
 }  // namespace cca

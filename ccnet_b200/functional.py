@@ -33,10 +33,12 @@ def _stream_ptr(device) -> int:
 
 
 def tc_eligible(B: int, Cq: int, C: int, H: int, W: int, dtype: torch.dtype) -> bool:
-    """True if the tcgen05 (channels-last) forward kernels cover this problem."""
+    """True if the tcgen05 (channels-last) kernels cover this problem, forward AND backward."""
     if dtype not in _DTYPES:
         return False
-    return capi.load().cca_b200_tc_supported(B, Cq, C, H, W, _DTYPES[dtype]) == 1
+    lib = capi.load()
+    return (lib.cca_b200_tc_supported(capi.CCA_WS_FORWARD, B, Cq, C, H, W, _DTYPES[dtype]) == 1
+            and lib.cca_b200_tc_supported(capi.CCA_WS_BACKWARD, B, Cq, C, H, W, _DTYPES[dtype]) == 1)
 
 
 def cca_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, impl: str = "auto"):
@@ -53,7 +55,7 @@ def cca_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, impl: str = "
     C = v.shape[1]
     dt = _DTYPES[q.dtype]
     flags = _IMPL_FLAGS[impl]
-    use_tc = impl in ("auto", "tc") and lib.cca_b200_tc_supported(B, Cq, C, H, W, dt) == 1
+    use_tc = impl in ("auto", "tc") and lib.cca_b200_tc_supported(capi.CCA_WS_FORWARD, B, Cq, C, H, W, dt) == 1
     if impl == "tc" and not use_tc:
         raise RuntimeError(f"ccnet_b200: tensor-core kernels do not cover q{tuple(q.shape)} v{tuple(v.shape)} {q.dtype}")
     if use_tc:
@@ -89,7 +91,11 @@ def cca_backward(dout, q, k, v, out, lse, impl: str = "auto"):
     C = v.shape[1]
     dt = _DTYPES[q.dtype]
     flags = _IMPL_FLAGS[impl]
-    use_tc = impl in ("auto", "tc") and lib.cca_b200_tc_supported(B, Cq, C, H, W, dt) == 1
+    if lse.dtype != torch.float32 or tuple(lse.shape) != (q.shape[0], q.shape[2], q.shape[3]) or lse.device != q.device:
+        raise RuntimeError("ccnet_b200: lse must be the forward's float32 [B,H,W] tensor on the same device")
+    if dout.device != q.device or out.device != q.device:
+        raise RuntimeError("ccnet_b200: dout/out must be on the same device as q,k,v")
+    use_tc = impl in ("auto", "tc") and lib.cca_b200_tc_supported(capi.CCA_WS_BACKWARD, B, Cq, C, H, W, dt) == 1
     if impl == "tc" and not use_tc:
         raise RuntimeError(f"ccnet_b200: tensor-core kernels do not cover q{tuple(q.shape)} v{tuple(v.shape)} {q.dtype}")
     if use_tc:

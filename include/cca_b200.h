@@ -21,7 +21,9 @@
  *   - every function returns CCA_OK (0) or a negative cca_status; the message of the
  *     last failure on the calling thread is available from cca_b200_last_error().
  *   - inputs are never written; outputs need no initialisation.
- *   - re-entrant: no global scratch; the caller supplies the (small) workspace.
+ *   - re-entrant: no global scratch; the caller supplies the (small) workspace.  Process-wide state is limited to
+ *     read-mostly caches (tensor maps, device attributes) and launch knobs read once from the environment.
+ *   - every compute entry point returns CCA_ERR_DEVICE unless the current device is compute capability 10.x.
  */
 #ifndef CCA_B200_H_
 #define CCA_B200_H_
@@ -33,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CCA_B200_VERSION 100 /* 0.1.0 */
+#define CCA_B200_VERSION 200 /* 0.2.0 */
 
 #if defined(__GNUC__)
 #define CCA_API __attribute__((visibility("default")))
@@ -81,8 +83,17 @@ CCA_API int cca_b200_device_ok(void);
 /* Number of kernels this library has launched in this process so far (for audits). */
 CCA_API unsigned long long cca_b200_launch_count(void);
 
-/* 1 if the tensor-core (tcgen05) forward covers this problem in NHWC layout, else 0. */
-CCA_API int cca_b200_tc_supported(int B, int Cq, int C, int H, int W, int dtype);
+/* 1 if the tensor-core (tcgen05) kernels cover this problem in NHWC layout on the current device, else 0.
+ * which = CCA_WS_FORWARD or CCA_WS_BACKWARD (the two directions have separate predicates).
+ * Covered: Cq in {16,32,48,64}, C % 64 == 0, H and W up to 896 (lines longer than 112 pixels are tiled). */
+CCA_API int cca_b200_tc_supported(int which, int B, int Cq, int C, int H, int W, int dtype);
+
+/* Introspection of the tensor-core kernels' work decomposition (host-only, no CUDA call; see csrc/cca_items.cuh):
+ * item_space: out8 = {total items, items per sample, column/first-key-block items, other column items, row items,
+ *                     tiles per column line, tiles per row line, padded tile length (80 or 112; 0 = not covered)}
+ * decode_item: out10 = {is_column, sample, line, query tile, key block, q0, lq, k0, lk, index inside the sample}. */
+CCA_API void cca_b200_item_space(int B, int H, int W, int *out8);
+CCA_API void cca_b200_decode_item(int B, int H, int W, int index, int *out10);
 
 /* Bytes of device workspace the forward / backward call needs for this problem. */
 CCA_API size_t cca_b200_workspace_bytes(int which, int B, int Cq, int C, int H, int W, int dtype);
