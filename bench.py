@@ -52,6 +52,62 @@ def alg_bytes(B, C, H, W, esize, fwd=True, bwd=True):
     return esize * N * ((2 * Cq + 2 * C) * (1 if fwd else 0) + (4 * Cq + 4 * C) * (1 if bwd else 0))
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pin this rank's CPU affinity (and with it the first-touch placement of the pinned host buffers it allocates next) to
+    the NUMA node its GPU hangs off.  8 ranks x 462 MB/step of pinned copies through one socket's memory controllers is what
+    capped the end-to-end curve at 8 GPUs in round 1 (GPUs 4-7 sit on NUMA node 1)."""
+    info = {"numa_node": None, "cpus": None}
+    try:
+        import torch
+        bdf = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+    except Exception:
+        bdf = None
+    try:
+        if bdf is None:
+            out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip()
+            bdf = out
+        bdf = bdf.lower()
+        if len(bdf.split(":")[0]) == 8:                    # nvidia-smi prints an 8-digit domain, sysfs a 4-digit one
+            bdf = bdf[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return info
+        cpulist = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info = {"numa_node": node, "cpus": len(allowed)}
+    except Exception:
+        pass
+    return info
+
+
+def ncu_traffic(dtype_name: str):
+    """DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of one op forward / backward, parsed from the committed
+    ncu summary of tools/run_op.py (BASELINE config 2, fp32).  Returns None when no capture matches."""
+    path = os.path.join(ROOT, "profiles", "r02_tc_ncu_summary.txt")
+    if dtype_name != "f32" or not os.path.exists(path):
+        return None
+    units = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}
+    tot = {"fwd": 0.0, "bwd": 0.0}
+    cur = None
+    for line in open(path):
+        if line.startswith("Kernel Name"):
+            name = line.split(None, 2)[2]
+            cur = "fwd" if ("stats_kernel" in name or "fwd_kernel" in name) else ("bwd" if "bwd" in name else None)
+        elif cur and (line.startswith("dram__bytes_read.sum") or line.startswith("dram__bytes_write.sum")):
+            f = line.split()
+            tot[cur] += float(f[1].replace(",", "")) * units.get(f[2].lower(), 1.0)
+    if tot["fwd"] == 0.0 or tot["bwd"] == 0.0:
+        return None
+    return {"fwd": tot["fwd"], "bwd": tot["bwd"], "source": "profiles/r02_tc_ncu_summary.txt"}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -101,7 +157,7 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_reference_run(steps: int, warmup: int, sample_b: int = 2):
+def cpu_reference_run(steps: int, warmup: int, sample_b: int = 8):
     """The reference module's CPU path (oracle module port, torch CPU ops, all host threads)."""
     from oracle.cca_oracle import CrissCrossAttentionOracle, rcca_forward
     try:
@@ -156,7 +212,8 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(), "note": "reference module CPU path (oracle port), bounded sample"},
-            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "host_logical_cpus": r["host_logical_cpus"],
+                             "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -197,6 +254,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (ccnet_b200 has no CPU path); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)      # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from ccnet_b200 import RCCA, capi, cca_backward, cca_forward
@@ -370,16 +428,16 @@ def run_ours(args):
     dom_is_bwd = b_avg >= f_avg
     dom_bytes, dom_ms = (bytes_b, b_avg) if dom_is_bwd else (bytes_f, f_avg)
     ach = dom_bytes / (dom_ms * 1e-3) / 1e9
-    # DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of one op call from the ncu --set full capture of
-    # tools/run_op.py committed as profiles/r01e_tc_ncu_summary.txt (B=8, C=512, 97x97, fp32, tensor-core kernels)
-    ncu_traffic = None
-    if (B, C, H, W) == (8, 512, 97, 97) and dtype == torch.float32 and op_layout == "channels_last":
-        ncu_traffic = {"fwd": 745.7e6, "bwd": 1574.4e6}
-    roofline = {"bound": "hbm", "kernel": "cca backward op (delta + column pass + row pass)" if dom_is_bwd
-                else "cca forward op (column pass + row pass)",
+    # DRAM traffic of one op call: parsed from the committed ncu --set full summary of tools/run_op.py (same shape / dtype)
+    traffic = None
+    if (B, C, H, W) == (8, 512, 97, 97) and op_layout == "channels_last":
+        traffic = ncu_traffic("f32" if dtype == torch.float32 else "bf16")
+    roofline = {"bound": "hbm", "kernel": "cca backward op (prep + one persistent item kernel)" if dom_is_bwd
+                else "cca forward op (statistics pre-pass + values kernel)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": (ncu_traffic["bwd" if dom_is_bwd else "fwd"] if ncu_traffic else None),
-                "traffic_source": "ncu --set full, profiles/r01e_tc_ncu_summary.txt (sum over the launches of one op call)",
+                "traffic": (traffic["bwd" if dom_is_bwd else "fwd"] if traffic else None),
+                "traffic_fwd": traffic["fwd"] if traffic else None, "traffic_bwd": traffic["bwd"] if traffic else None,
+                "traffic_source": (traffic["source"] + " (ncu --set full; sum over the launches of one op call)") if traffic else None,
                 "peak_source": peak_src, "launches_per_op": nb if dom_is_bwd else nf,
                 "op_fwd": {"ms": f_avg, "ms_min": f_min, "alg_bytes": bytes_f, "gbs": bytes_f / f_avg / 1e6,
                            "frac": bytes_f / f_avg / 1e6 / peak, "launches": nf},
@@ -410,7 +468,8 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         r = cpu_reference_run(3, 1)
-        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "host_logical_cpus": r["host_logical_cpus"],
+               "kind": "port", "sample": r["sample"]}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -420,7 +479,8 @@ def run_ours(args):
                            "op_layout": op_layout,
                            "l2": "inputs larger than L2: one op fwd+bwd touches q,k,v,dout,out,dq,dk,dv = 1.04 GB vs 126 MB "
                                  "L2 (no explicit flush in the timed loop); the per-op roofline timings flush 256 MB explicitly",
-                           "parallelism": f"dp{world} (image-sharded, DDP grad all-reduce only)"},
+                           "parallelism": f"dp{world} (image-sharded, DDP grad all-reduce only)",
+                           "host_binding": numa},
                 "clocks": clk.summary(), "e2e": e2e, "module": module, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))

@@ -26,8 +26,14 @@ SYMBOLS = {
     "cca_b200_launch_count": (ctypes.c_ulonglong, []),
     "cca_b200_tc_supported": (_i, [_i] * 7),
     "cca_b200_item_space": (None, [_i] * 3 + [ctypes.POINTER(_i)]),
-    "cca_b200_decode_item": (None, [_i] * 4 + [ctypes.POINTER(_i)]),
+    "cca_b200_decode_item": (None, [_i] * 5 + [ctypes.POINTER(_i)]),
     "cca_b200_workspace_bytes": (_sz, [_i] * 7),
+    "cca_b200_qkv_supported": (_i, [_i, _i]),
+    "cca_b200_qkv_workspace_bytes": (_sz, [_i, _i]),
+    "cca_b200_qkv_project": (_i, [_vp] * 11 + [_sz, ctypes.c_longlong, _i, _i, _vp]),
+    "cca_b200_qkv_project_dgrad": (_i, [_vp] * 9 + [_sz, ctypes.c_longlong, _i, _i, _i, _vp]),
+    "cca_b200_qkv_wgrad_supported": (_i, [_i, _i]),
+    "cca_b200_qkv_project_wgrad": (_i, [_vp] * 9 + [ctypes.c_longlong, _i, _i, _vp]),
     "cca_b200_forward": (_i, [_vp] * 6 + [_sz] + [_i] * 6 + [_u, _vp]),
     "cca_b200_backward": (_i, [_vp] * 10 + [_sz] + [_i] * 6 + [_u, _vp]),
     "cca_b200_forward_host": (_i, [_vp] * 5 + [_i] * 6 + [_u]),

@@ -46,7 +46,7 @@ int env_int(const char *name, int dflt, int lo, int hi)
     return v < lo || v > hi ? dflt : v;
 }
 constexpr int kUnset = -1000;
-std::atomic<int> g_pdl{kUnset}, g_zero_ahead{kUnset}, g_delta{kUnset};
+std::atomic<int> g_pdl{kUnset}, g_zero_ahead{kUnset}, g_delta{kUnset}, g_lag{kUnset}, g_hints{kUnset};
 int knob(std::atomic<int> &g, const char *name, int dflt, int lo, int hi)
 {
     int v = g.load(std::memory_order_relaxed);
@@ -60,10 +60,14 @@ int knob(std::atomic<int> &g, const char *name, int dflt, int lo, int hi)
 int tc_pdl() { return knob(g_pdl, "CCA_B200_PDL", 1, 0, 1); }
 int tc_zero_ahead() { return knob(g_zero_ahead, "CCA_B200_ZERO_AHEAD", 1, 1, 4); }
 int tc_delta_mode() { return knob(g_delta, "CCA_B200_DELTA", -1, -1, 1); }
+int tc_lag() { return knob(g_lag, "CCA_B200_LAG", -1, -1, 1); }
+int tc_l2_hints() { return knob(g_hints, "CCA_B200_L2HINT", 1, 0, 1); }
 #ifdef CCA_DEBUG_HOOKS
 void set_tc_pdl(int on) { g_pdl.store(on ? 1 : 0); }
 void set_tc_zero_ahead(int n) { g_zero_ahead.store(n < 1 ? 1 : (n > 4 ? 4 : n)); }
 void set_tc_delta_mode(int m) { g_delta.store(m < -1 || m > 1 ? -1 : m); }
+void set_tc_lag(int v) { g_lag.store(v < -1 || v > 1 ? -1 : v); }
+void set_tc_l2_hints(int v) { g_hints.store(v ? 1 : 0); }
 #endif
 }  // namespace cca
 
@@ -79,6 +83,8 @@ CCA_API void cca_b200__set_bwd_debug_buffer(void *p) { set_tc_bwd_debug_buffer(p
 CCA_API void cca_b200__set_pdl(int on) { set_tc_pdl(on); }
 CCA_API void cca_b200__set_zero_ahead(int n) { set_tc_zero_ahead(n); }
 CCA_API void cca_b200__set_delta_mode(int m) { set_tc_delta_mode(m); }
+CCA_API void cca_b200__set_lag(int v) { set_tc_lag(v); }
+CCA_API void cca_b200__set_l2_hints(int v) { set_tc_l2_hints(v); }
 #endif
 const char *cca_b200_last_error(void) { return g_err; }
 const char *cca_b200_strerror(int s)
@@ -159,10 +165,10 @@ void cca_b200_item_space(int B, int H, int W, int *out8)
     out8[0] = s.total; out8[1] = s.per_sample; out8[2] = s.seg0; out8[3] = s.seg1; out8[4] = s.seg2;
     out8[5] = s.col.nt; out8[6] = s.row.nt; out8[7] = tc::lk_for(tc::max_tile(s));
 }
-void cca_b200_decode_item(int B, int H, int W, int index, int *out10)
+void cca_b200_decode_item(int B, int H, int W, int index, int lagged, int *out10)
 {
     const tc::ItemSpace s = tc::make_space(B, H, W);
-    const tc::Item it = tc::decode_item(s, index);
+    const tc::Item it = tc::decode_item_order(s, index, lagged);
     out10[0] = it.col; out10[1] = it.b; out10[2] = it.line; out10[3] = it.iq; out10[4] = it.ik;
     out10[5] = it.q0; out10[6] = it.lq; out10[7] = it.k0; out10[8] = it.lk; out10[9] = it.j;
 }
@@ -238,6 +244,81 @@ int cca_b200_backward(const void *dout, const void *q, const void *k, const void
                                   reinterpret_cast<cudaStream_t>(stream), &why);
     if (e != cudaSuccess) return cuda_fail(e, "simt_backward");
     return CCA_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// 1x1 Q/K/V projections (functions.py:29,32,35) as tensor-core GEMMs on the channels-last view
+// ---------------------------------------------------------------------------------------
+int cca_b200_qkv_supported(int C, int Cq)
+{
+    if (C <= 0 || Cq <= 0) return 0;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0 && device_major() != 10) return 0;
+    return qkv_gemm_supported(C, Cq) ? 1 : 0;
+}
+size_t cca_b200_qkv_workspace_bytes(int C, int Cq) { return C > 0 && Cq > 0 ? qkv_gemm_workspace(C, Cq) : 0; }
+
+int cca_b200_qkv_project(const float *x, const float *wq, const float *bq, const float *wk, const float *bk, const float *wv,
+                         const float *bv, float *q, float *k, float *v, void *ws, size_t ws_bytes, long long pixels, int C, int Cq,
+                         void *stream)
+{
+    if (!x || !wq || !bq || !wk || !bk || !wv || !bv || !q || !k || !v || !ws) return fail(CCA_ERR_INVALID, "null pointer%s%s");
+    if (pixels <= 0 || pixels >= (1ll << 31) || C <= 0 || Cq <= 0) return fail(CCA_ERR_INVALID, "bad dimension%s%s");
+    if (ws_bytes < qkv_gemm_workspace(C, Cq)) return fail(CCA_ERR_WORKSPACE, "projection workspace too small%s%s");
+    int rc = check_device();
+    if (rc) return rc;
+    if (!qkv_gemm_supported(C, Cq)) return fail(CCA_ERR_UNSUPPORTED, "projection GEMM needs C %% 64 == 0 and Cq %% 64 == 0%s%s");
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+         reinterpret_cast<uintptr_t>(ws)) & 15)
+        return fail(CCA_ERR_INVALID, "projection GEMM needs 16-byte aligned tensors%s%s");
+    const char *why = "";
+    cudaError_t e = qkv_project(x, wq, bq, wk, bk, wv, bv, q, k, v, ws, (long)pixels, C, Cq, reinterpret_cast<cudaStream_t>(stream), &why);
+    if (e != cudaSuccess) return cuda_fail(e, why && *why ? why : "qkv_project");
+    return CCA_OK;
+}
+
+int cca_b200_qkv_project_dgrad(const float *dq, const float *dk, const float *dv, const float *wq, const float *wk, const float *wv,
+                               const float *scale, float *dx, void *ws, size_t ws_bytes, long long pixels, int C, int Cq,
+                               int accumulate, void *stream)
+{
+    if (!dq || !dk || !dv || !wq || !wk || !wv || !dx || !ws) return fail(CCA_ERR_INVALID, "null pointer%s%s");
+    if (pixels <= 0 || pixels >= (1ll << 31) || C <= 0 || Cq <= 0) return fail(CCA_ERR_INVALID, "bad dimension%s%s");
+    if (ws_bytes < qkv_gemm_workspace(C, Cq)) return fail(CCA_ERR_WORKSPACE, "projection workspace too small%s%s");
+    int rc = check_device();
+    if (rc) return rc;
+    if (!qkv_gemm_supported(C, Cq)) return fail(CCA_ERR_UNSUPPORTED, "projection GEMM needs C %% 64 == 0 and Cq %% 64 == 0%s%s");
+    if ((reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv) |
+         reinterpret_cast<uintptr_t>(ws)) & 15)
+        return fail(CCA_ERR_INVALID, "projection GEMM needs 16-byte aligned tensors%s%s");
+    const char *why = "";
+    cudaError_t e = qkv_project_dgrad(dq, dk, dv, wq, wk, wv, scale, dx, ws, (long)pixels, C, Cq, accumulate,
+                                      reinterpret_cast<cudaStream_t>(stream), &why);
+    if (e != cudaSuccess) return cuda_fail(e, why && *why ? why : "qkv_project_dgrad");
+    return CCA_OK;
+}
+
+int cca_b200_qkv_project_wgrad(const float *x, const float *dq, const float *dk, const float *dv, const float *scale, float *dwq,
+                               float *dwk, float *dwv, float *db, long long pixels, int C, int Cq, void *stream)
+{
+    if (!x || !dq || !dk || !dv || !dwq || !dwk || !dwv) return fail(CCA_ERR_INVALID, "null pointer%s%s");
+    if (pixels <= 0 || pixels >= (1ll << 31) || C <= 0 || Cq <= 0) return fail(CCA_ERR_INVALID, "bad dimension%s%s");
+    int rc = check_device();
+    if (rc) return rc;
+    if (!qkv_wgrad_supported(C, Cq)) return fail(CCA_ERR_UNSUPPORTED, "weight-gradient GEMM needs C %% 256 == 0 and Cq %% 64 == 0%s%s");
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv) |
+         reinterpret_cast<uintptr_t>(dwq) | reinterpret_cast<uintptr_t>(dwk) | reinterpret_cast<uintptr_t>(dwv)) & 15)
+        return fail(CCA_ERR_INVALID, "weight-gradient GEMM needs 16-byte aligned tensors%s%s");
+    const char *why = "";
+    cudaError_t e = qkv_project_wgrad(x, dq, dk, dv, scale, dwq, dwk, dwv, db, (long)pixels, C, Cq, reinterpret_cast<cudaStream_t>(stream), &why);
+    if (e != cudaSuccess) return cuda_fail(e, why && *why ? why : "qkv_project_wgrad");
+    return CCA_OK;
+}
+int cca_b200_qkv_wgrad_supported(int C, int Cq)
+{
+    if (C <= 0 || Cq <= 0) return 0;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0 && device_major() != 10) return 0;
+    return qkv_wgrad_supported(C, Cq) ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -52,18 +52,36 @@ size_t tc_backward_workspace(Dims d);
 cudaError_t tc_backward(const void *dout, const void *q, const void *k, const void *v, const void *out, const float *lse,
                         void *dq, void *dk, void *dv, void *ws, Dims d, int dtype, cudaStream_t st, const char **why);
 
+// tcgen05 GEMMs of the 1x1 Q/K/V projections (cca_gemm.cu), fp32 channels-last tensors as [pixels, channels] matrices
+bool qkv_gemm_supported(int C, int Cq);
+size_t qkv_gemm_workspace(int C, int Cq);
+cudaError_t qkv_project(const float *x, const float *wq, const float *bq, const float *wk, const float *bk, const float *wv, const float *bv,
+                        float *q, float *k, float *v, void *ws, long P, int C, int Cq, cudaStream_t st, const char **why);
+cudaError_t qkv_project_dgrad(const float *dq, const float *dk, const float *dv, const float *wq, const float *wk, const float *wv,
+                              const float *scale, float *dx, void *ws, long P, int C, int Cq, int accumulate, cudaStream_t st,
+                              const char **why);
+bool qkv_wgrad_supported(int C, int Cq);
+cudaError_t qkv_project_wgrad(const float *x, const float *dq, const float *dk, const float *dv, const float *scale, float *dwq,
+                              float *dwk, float *dwv, float *db, long P, int C, int Cq, cudaStream_t st, const char **why);
+
 void count_launch(int n = 1);
 // Launch knobs of the tensor-core kernels, read once from the environment (std::atomic, safe under DataParallel threads):
 //   CCA_B200_PDL = 0/1        programmatic dependent launch between the launches of one op (default 1)
 //   CCA_B200_ZERO_AHEAD = n   the items of sample b clear the outputs of sample b+n (default 1)
 //   CCA_B200_DELTA = -1/0/1   backward: -1 automatic, 0 every item computes delta, 1 column items produce it for the sample
+//   CCA_B200_LAG = 0/1        item order: consumers of a sample trail its producers by one block (default 1 forward, 0 backward)
+//   CCA_B200_L2HINT = 0/1     L2 eviction hints on the bulk copies (default 1)
 int tc_pdl();
 int tc_zero_ahead();
 int tc_delta_mode();
+int tc_lag();          // -1 = per-kernel default
+int tc_l2_hints();
 #ifdef CCA_DEBUG_HOOKS
 void set_tc_pdl(int on);
 void set_tc_zero_ahead(int n);
 void set_tc_delta_mode(int m);
+void set_tc_lag(int v);
+void set_tc_l2_hints(int v);
 void set_tc_debug_buffer(void *p);
 void set_tc_bwd_debug_buffer(void *p);
 #endif

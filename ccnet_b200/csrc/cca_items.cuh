@@ -11,9 +11,12 @@
 //
 // Item order (static, round-robin over the persistent CTAs): sample by sample, so that the second touch of a sample's
 // tensors (other direction / other tile) finds them in L2; inside a sample
-//   segment 0: column items with ik == 0   (the backward's delta producers come first: everything another item of the
-//   segment 1: column items with ik >= 1    sample may wait for has a LOWER index -> no cyclic waits)
-//   segment 2: row items
+//   segment 0: column items with ik == 0   ("producers": they STORE the output tiles / publish delta; everything another
+//   segment 1: column items with ik >= 1    item of the sample may wait for has a LOWER index -> no cyclic waits)
+//   segment 2: row items                   ("consumers": they ADD onto what the producers stored)
+// decode_item walks the samples one after the other (P(0) C(0) P(1) C(1) ...); decode_item_lagged lets the consumers of a
+// sample trail its producers by one block (P(0) P(1) C(0) P(2) C(1) ... C(B-1)): by the time a consumer wants to add onto
+// the output, the producers of its sample have long finished, at the price of a larger L2 working set.
 // Host + device code: the same functions are unit-tested on the CPU (tests/test_items_host.py via cca_b200_debug_item).
 #pragma once
 
@@ -109,6 +112,27 @@ CCA_HD Item decode_item(const ItemSpace &s, int idx)
     it.lk = g->L - it.k0 < g->tl ? g->L - it.k0 : g->tl;
     return it;
 }
+
+// item j (0 .. per_sample-1) of sample b
+CCA_HD Item decode_item_in_sample(const ItemSpace &s, int b, int j) { return decode_item(s, b * s.per_sample + j); }
+
+// P(0) | P(1) C(0) | P(2) C(1) | ... | P(B-1) C(B-2) | C(B-1)      P(b) = segment 0 of sample b, C(b) = segments 1, 2
+CCA_HD Item decode_item_lagged(const ItemSpace &s, int idx)
+{
+    const int np = s.seg0, nc = s.per_sample - s.seg0;
+    if (idx < np) return decode_item_in_sample(s, 0, idx);
+    const int x = idx - np;
+    const int grp = x / s.per_sample, rem = x - grp * s.per_sample;
+    if (grp < s.B - 1) {
+        if (rem < np) return decode_item_in_sample(s, grp + 1, rem);
+        return decode_item_in_sample(s, grp, np + (rem - np));
+    }
+    (void)nc;
+    return decode_item_in_sample(s, s.B - 1, np + rem);
+}
+CCA_HD Item decode_item_order(const ItemSpace &s, int idx, int lag) { return lag ? decode_item_lagged(s, idx) : decode_item(s, idx); }
+// segment-0 items ("producers") of a sample
+CCA_HD bool is_producer(const Item &it) { return it.col && it.ik == 0; }
 
 // pixel index (b, h, w) -> flat [B,H,W] of query row r of an item
 CCA_HD long item_pixel(const ItemSpace &s, const Item &it, int r)

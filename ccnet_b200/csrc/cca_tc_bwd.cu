@@ -17,8 +17,11 @@
 // block do, publish it through global memory and a per-sample counter, and the other items of the sample wait for that counter
 // right before their dS phase (such items always have a higher index than the producers: no cyclic waits).
 //
-// Zero-ahead (dq, dk, dv need no initialisation by the caller): as in the forward (cca_tc_fwd.cu), the items of sample b
-// clear 1/per_sample of sample b+ahead's slices, a prep kernel clears the first `ahead` samples and the counters.
+// Output path (dq, dk, dv need no initialisation by the caller).  One tile per line (H, W <= 112): as in the forward
+// (cca_tc_fwd.cu) the column items STORE their tiles, the row items ADD onto them (TMA reduce-add) once the per-sample counter
+// cdone[b] says every column item of the sample has completed its stores.  Tiled lines: several items contribute to the same
+// dk / dv rows, so everything is added: the items of sample b first clear 1/per_sample of sample b+ahead's slices (zero-ahead,
+// bulk copies of a zero tile, counter zdone), a prep kernel clears the first `ahead` samples and the counters.
 //
 // All GEMMs run as bf16x3 split MMAs (hi*hi + hi*lo + lo*hi) with fp32 accumulation in TMEM (single bf16 MMAs for bf16 I/O).
 // The same operand planes serve several GEMMs: planes over channels are a K-major operand when the contraction runs over
@@ -46,6 +49,10 @@ struct BwdParams {
     unsigned int *zdone;       // [B] zero shares of sample b completed
     unsigned int *ddone;       // [B] delta producers of sample b done (delta_mode 1)
     int delta_mode;            // 0: every item computes its own delta; 1: column / first-key-block items produce, the rest wait
+    int out_mode;              // 1: producers store, consumers add after cdone (one tile per line); 0: zero-ahead, everything adds
+    unsigned int *cdone;       // [B] producer items of sample b whose stores have completed (out_mode 1)
+    int lag;                   // item order (cca_items.cuh): 1 = consumers trail the producers by one block
+    int hints;                 // L2 eviction hints on the bulk copies
     uint8_t *dq, *dk, *dv;
     long sb_q, sb_v;           // bytes per sample of dq (= dk) and dv
     long share_q, share_v;     // zero share per item
@@ -164,7 +171,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
     const int KQ = p.Cq / 16;
     const int NO = NCH + 2;                   // output tiles per item: dV chunks, dQ, dK
     const int nk = p.sp.total > (int)blockIdx.x ? (p.sp.total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    auto item_of = [&](int k) { return decode_item(p.sp, (int)blockIdx.x + k * (int)gridDim.x); };
+    auto item_of = [&](int k) { return decode_item_order(p.sp, (int)blockIdx.x + k * (int)gridDim.x, p.lag); };
 
     if (tid == 0) {
         for (int i = 0; i < kNLd; ++i) {
@@ -199,7 +206,8 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                 uint32_t g = 0;
                 int dbg_n = 0;
                 (void)dbg_n;
-                auto emit = [&](const CUtensorMap *mc, const CUtensorMap *mr, int c0, const Item &it, int start) {
+                const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+                auto emit = [&](const CUtensorMap *mc, const CUtensorMap *mr, int c0, const Item &it, int start, bool last_use = false) {
                     const CUtensorMap *m = it.col ? mc : mr;
                     const int cw = it.col ? it.line : start, ch = it.col ? start : it.line;
                     const int slot = g % kNLd;
@@ -207,8 +215,14 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                     CCA_STAMP(0);
                     uint8_t *dst = smem + S::off_ld + slot * T::kSlot;
                     mbar_expect_tx(&bars[B_LD_FULL + slot], T::kSlot);
-                    tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, it.b);
-                    if constexpr (!BF) tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, it.b);
+                    if (p.hints) {          // what the sample's consumers read again stays; O and the consumers' own operands stream
+                        const uint64_t pol = (is_producer(it) && !last_use) ? pol_keep : pol_stream;
+                        tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, it.b, pol);
+                        if constexpr (!BF) tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, it.b, pol);
+                    } else {
+                        tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, it.b);
+                        if constexpr (!BF) tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, it.b);
+                    }
                     ++g;
                 };
                 // ring:  Q0 K0 | (V dO [O])* Q1 K1 Q0 K0 | (V dO [O])* Q2 K2 Q1 K1 | ...   (S of the next item is issued while the
@@ -224,7 +238,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                     for (int n = 0; n < NCH; ++n) {
                         emit(&mvc, &mvr, n * kNC, it, it.k0);
                         emit(&mdoc, &mdor, n * kNC, it, it.q0);
-                        if (calc) emit(&moc, &mor, n * kNC, it, it.q0);
+                        if (calc) emit(&moc, &mor, n * kNC, it, it.q0, p.delta_mode == 1);   // (mode 1: nobody reads O again)
                     }
                     if (k + 1 < nk) {
                         const Item nx = item_of(k + 1);
@@ -326,13 +340,15 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             // =============================== store warp (one lane): the output staging slot <-> global ===============================
             if (lane == 0) {
                 uint8_t *slot = smem + S::off_out;
-                pdl_wait();                                // prep kernel complete: counters and the first samples of dq/dk/dv cleared
+                pdl_wait();                                // prep kernel complete: counters (and the first samples of dq/dk/dv) cleared
+                const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
                 int pending = -1;
                 uint32_t c = 0;
                 for (int k = 0; k < nk; ++k) {
                     const Item it = item_of(k);
+                    const bool prod = p.out_mode == 1 && is_producer(it);
                     const int zb = it.b + p.ahead;
-                    if (zb < p.sp.B) {                     // zero-ahead: this item's share of sample zb (dq, dk, dv)
+                    if (p.out_mode == 0 && zb < p.sp.B) {  // zero-ahead: this item's share of sample zb (dq, dk, dv)
                         uint8_t *dst[3] = {p.dq + (long)zb * p.sb_q, p.dk + (long)zb * p.sb_q, p.dv + (long)zb * p.sb_v};
                         for (int t = 0; t < 3; ++t) {
                             const long sh = t < 2 ? p.share_q : p.share_v, sb = t < 2 ? p.sb_q : p.sb_v;
@@ -360,14 +376,35 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                                 publish_count(p.zdone + pending);
                                 pending = -1;
                             }
-                            if (it.b >= p.ahead) {
+                            if (p.out_mode == 0 && it.b >= p.ahead) {
                                 wait_count(p.zdone + it.b, (unsigned)p.sp.per_sample);
                                 fence_proxy_async_all();
                             }
+                            if (p.out_mode == 1 && !prod) {    // every producer of this sample has stored its tiles
+                                wait_count(p.cdone + it.b, (unsigned)p.sp.seg0);
+                                fence_proxy_async_all();
+                            }
                         }
-                        tma_reduce_add_4d(m, slot, c0, cw, ch, it.b);
-                        if constexpr (!BF) tma_reduce_add_4d(m, slot + T::kTile, c0 + 32, cw, ch, it.b);
+                        if (prod) {
+                            if (p.hints) {
+                                tma_store_4d(m, slot, c0, cw, ch, it.b, pol_keep);
+                                if constexpr (!BF) tma_store_4d(m, slot + T::kTile, c0 + 32, cw, ch, it.b, pol_keep);
+                            } else {
+                                tma_store_4d(m, slot, c0, cw, ch, it.b);
+                                if constexpr (!BF) tma_store_4d(m, slot + T::kTile, c0 + 32, cw, ch, it.b);
+                            }
+                        } else if (p.hints && p.out_mode == 1) {   // the one and only add onto these lines: they are final
+                            tma_reduce_add_4d(m, slot, c0, cw, ch, it.b, pol_stream);
+                            if constexpr (!BF) tma_reduce_add_4d(m, slot + T::kTile, c0 + 32, cw, ch, it.b, pol_stream);
+                        } else {
+                            tma_reduce_add_4d(m, slot, c0, cw, ch, it.b);
+                            if constexpr (!BF) tma_reduce_add_4d(m, slot + T::kTile, c0 + 32, cw, ch, it.b);
+                        }
                         tma_store_commit();
+                    }
+                    if (prod) {                            // publish: all stores of this item have completed
+                        tma_store_wait_all<0>();
+                        publish_count(p.cdone + it.b);
                     }
                 }
                 tma_store_wait_all<0>();
@@ -438,8 +475,11 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             const bool calc = calc_delta(p, it);
             const bool rvalid = r < it.lq;
             const long pix = item_pixel(p.sp, it, rvalid ? r : 0);
-            const float lse2 = rvalid ? p.lse[pix] * kLog2e : 0.f;
+            const float nlse = rvalid ? -p.lse[pix] * kLog2e : -INFINITY;     // rows beyond the tile: P = exp2(-inf) = 0
             const int self = it.col ? it.q0 + r - it.k0 : -1;
+            // predicated path only for the 16-key chunks holding the tail of the key block or the self entry of one of this
+            // warp's 32 query pixels (warp-uniform test); see cca_tc_fwd.cu
+            const int sw0 = it.col ? it.q0 - it.k0 + 32 * (warp & 3) : -(1 << 20);
             uint8_t *ph = smem + S::off_p + r * 16, *pl = ph + T::kPP * T::kPlane;
             // ---------------- P = exp(S - lse)
             const uint32_t tsd = tl + (k & 1) * 128;           // S(k) / dP(k) buffer
@@ -459,11 +499,15 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
 #pragma unroll
                 for (int e = 0; e < 16; ++e) s[e] = nx[e];
                 if (c0 + 16 < LK) tmem_ld16(tsd + c0 + 16, reinterpret_cast<uint32_t *>(nx));
+                if (!((c0 + 16 > it.lk) || (c0 + 16 > sw0 && c0 < sw0 + 32))) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const int j = c0 + e;
-                    const bool ok = rvalid && j < it.lk && j != self;
-                    s[e] = ok ? exp2f(s[e] * kLog2e - lse2) : 0.f;
+                    for (int e = 0; e < 16; ++e) s[e] = exp2f(fmaf(s[e], kLog2e, nlse));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int j = c0 + e;
+                        s[e] = (j < it.lk && j != self) ? exp2f(fmaf(s[e], kLog2e, nlse)) : 0.f;
+                    }
                 }
                 if (r < LK) {
 #pragma unroll
@@ -526,9 +570,8 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const float p0 = bf_lo(hw[e]) + bf_lo(lw[e]), p1 = bf_hi(hw[e]) + bf_hi(lw[e]);
-                            // P == 0 marks a masked / padded entry: its dP may hold anything (rows of a neighbouring tile)
-                            ds[2 * e] = p0 != 0.f ? p0 * (dp[h * 8 + 2 * e] - dl) : 0.f;
-                            ds[2 * e + 1] = p1 != 0.f ? p1 * (dp[h * 8 + 2 * e + 1] - dl) : 0.f;
+                            ds[2 * e] = p0 * (dp[h * 8 + 2 * e] - dl);       // masked / padded entries have P == 0 exactly
+                            ds[2 * e + 1] = p1 * (dp[h * 8 + 2 * e + 1] - dl);
                         }
                         if constexpr (BF) {
                             *reinterpret_cast<uint4 *>(ph + kc * T::kPlane) =
@@ -622,29 +665,38 @@ cudaError_t launch_bwd(const void *dout, const void *q, const void *k, const voi
     CUtensorMap m[16];
     const void *base[8] = {q, k, v, dout, out, dq, dk, dv};
     const int ch[8] = {d.Cq, d.Cq, d.C, d.C, d.C, d.Cq, d.Cq, d.C};
+    BwdParams p;
+    p.sp = make_space(d.B, d.H, d.W);
     for (int t = 0; t < 8; ++t)
-        for (int r = 0; r < 2; ++r)
-            if (!get_map(&m[2 * t + r], base[t], d.B, d.H, d.W, ch[t], LK, r == 0, BF)) {
+        for (int r = 0; r < 2; ++r) {
+            // loads: LK-pixel boxes (zero-filled past the image); outputs: boxes of exactly one tile of the direction
+            const int rows = t < 5 ? LK : (r == 0 ? p.sp.col.tl : p.sp.row.tl);
+            if (!get_map(&m[2 * t + r], base[t], d.B, d.H, d.W, ch[t], rows, r == 0, BF)) {
                 if (why) *why = "cuTensorMapEncodeTiled failed";
                 return cudaErrorInvalidValue;
             }
-    BwdParams p;
-    p.sp = make_space(d.B, d.H, d.W);
+        }
     p.C = d.C; p.Cq = d.Cq;
     p.npix = (long)d.B * d.H * d.W;
     p.lse = lse; p.delta = delta;
-    p.zdone = counters; p.ddone = counters + d.B;
+    p.zdone = counters; p.ddone = counters + d.B; p.cdone = counters + 2 * d.B;
     p.delta_mode = delta_mode;
+    const bool one_tile = p.sp.col.nt == 1 && p.sp.row.nt == 1;
+    p.out_mode = one_tile ? 1 : 0;
+    p.lag = tc_lag() == 1 ? 1 : 0;                 // default (-1): sample after sample (the backward's per-sample working set is
+                                                   // too large for two samples to share L2)
+    p.hints = tc_l2_hints();
     p.dq = reinterpret_cast<uint8_t *>(dq); p.dk = reinterpret_cast<uint8_t *>(dk); p.dv = reinterpret_cast<uint8_t *>(dv);
     const long es = BF ? 2 : 4;
     p.sb_q = (long)d.H * d.W * d.Cq * es; p.sb_v = (long)d.H * d.W * d.C * es;
     p.share_q = zero_share_bytes(p.sb_q, p.sp.per_sample); p.share_v = zero_share_bytes(p.sb_v, p.sp.per_sample);
     p.ahead = ahead;
     p.dbg = g_bwd_dbg;
-    // prologue: counters and the first `ahead` samples of the outputs
-    const int head = ahead < d.B ? ahead : d.B;
-    cca_bwd_prep_kernel<<<sm_count(), 256, 0, st>>>(reinterpret_cast<uint4 *>(dq), reinterpret_cast<uint4 *>(dk), reinterpret_cast<uint4 *>(dv),
-                                                    head * p.sb_q / 16, head * p.sb_v / 16, counters, 2 * d.B);
+    // prologue: counters and (zero-ahead mode) the first `ahead` samples of the outputs
+    const int head = p.out_mode == 1 ? 0 : (ahead < d.B ? ahead : d.B);
+    cca_bwd_prep_kernel<<<p.out_mode == 1 ? 1 : sm_count(), 256, 0, st>>>(
+        reinterpret_cast<uint4 *>(dq), reinterpret_cast<uint4 *>(dk), reinterpret_cast<uint4 *>(dv), head * p.sb_q / 16,
+        head * p.sb_v / 16, counters, 3 * d.B);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -672,11 +724,11 @@ void set_tc_bwd_debug_buffer(void *p) { g_bwd_dbg = reinterpret_cast<long long *
 
 bool tc_backward_supported(Dims d, int dtype) { return tc::shape_supported(d, dtype); }
 
-// Workspace of the backward: delta [B,H,W] fp32, then 2*B unsigned counters.
+// Workspace of the backward: delta [B,H,W] fp32, then 3*B unsigned counters.
 size_t tc_backward_workspace(Dims d)
 {
     const size_t delta = ((size_t)d.B * d.H * d.W * sizeof(float) + 15) & ~(size_t)15;
-    return delta + (((size_t)2 * d.B * sizeof(unsigned int) + 15) & ~(size_t)15);
+    return delta + (((size_t)3 * d.B * sizeof(unsigned int) + 15) & ~(size_t)15);
 }
 
 // all tensors channels-last (NHWC), fp32 or bf16

@@ -12,13 +12,16 @@
 // than one tile are just more items.  ONE persistent launch walks the items sample by sample: the second direction of a
 // sample finds q,k,v in L2 and adds onto output lines that are still L2-resident, so DRAM sees q,k,v once and out once.
 //
-// Zero-ahead: `out` needs no initialisation by the caller.  The statistics kernel clears the first `ahead` samples; every
-// item of sample b clears 1/per_sample of sample b+ahead (bulk copies of a zero tile, issued by the store warp before the
-// item's first store) and bumps zdone[b+ahead] once those copies have completed; the first reduce-add of an item of sample
-// b waits for zdone[b] == per_sample.  Only items with a LOWER index are ever waited for, and each persistent CTA walks its
-// items in increasing order, so the wait cannot cycle.  The two contributions of a pixel (column item, row item) are added
-// onto an exact zero: the result does not depend on their order (bit-reproducible); with key-block tiling (lines > 112
-// pixels) a pixel gets 2*nt contributions whose order is not fixed (last-bit differences between runs).
+// Two touches per output element, ordered (the L2 write path is the scarce resource: ~5 TB/s for plain stores, ~4 TB/s for
+// reduce-adds that hit L2, 2.4 TB/s when they miss -- tools/tma_red_bench.cu): the "producer" items of a sample (column
+// lines, first key block) STORE their tile, every other item of the sample ADDS onto it with a TMA reduce-add once the
+// per-sample counter cdone[b] says all producers have completed their stores.  Items are walked in the lagged order of
+// cca_items.cuh -- P(0) | P(1) C(0) | P(2) C(1) ... -- so a consumer practically never waits; only items with a LOWER index
+// are ever waited for and each persistent CTA walks its items in increasing order, so the wait cannot cycle.  Store / add
+// boxes are exactly one tile long (tensor maps with box = tile length), so a store never touches a neighbouring tile.
+// L2 eviction hints keep what the consumers will touch again (producer loads and stores: evict_last) and let the rest
+// stream (consumer loads: evict_first).  With one tile per line every output element is one store plus one add: the result
+// is bit-reproducible; with key-block tiling a pixel gets 2*nt-1 adds whose order is not fixed (last-bit differences).
 //
 // Roles (warpgroups, registers rebalanced with setmaxnreg), software-pipelined across items:
 //   TMA producer (1 thread)   : 4-D tiled loads [LK px][32 ch] fp32 / [LK px][64 ch] bf16, SWIZZLE_128B, OOB pixels
@@ -31,7 +34,7 @@
 //   softmax group (128 thr)   : one pass over the S row in TMEM (lane = query pixel): P = exp2(S log2e - lse2) -> TMEM as
 //                               packed bf16 (hi/lo); also writes the final lse (row items, first key block).
 //   epilogue group (128 thr)  : per chunk TMEM -> swizzled staging tile (no scaling left to do).
-//   store warp (1 lane)       : zero-ahead, TMA reduce-add of the staged tiles, counters.
+//   store warp (1 lane)       : TMA store / reduce-add of the staged tiles, per-sample counters.
 #include "cca_items.cuh"
 #include "cca_tc_common.cuh"
 
@@ -44,7 +47,6 @@ constexpr int kTmemP = 128, kTmemO = 384, kNOB = 2;
 constexpr int kRegsSoft = 104, kRegsEpi = 128, kRegsConvF = 88;
 static_assert(reg_pool_ok(kRegsSoft, kRegsEpi, kRegsConvF), "setmaxnreg pool");
 constexpr int kNOut = 2;            // staging slots
-constexpr int kZeroBuf = 2048;      // zero tile for the zero-ahead bulk copies
 
 struct FwdParams {
     ItemSpace sp;
@@ -52,11 +54,9 @@ struct FwdParams {
     long npix;
     const float *parts;    // [nparts][B*H*W] partial log2-sum-exp2 (statistics pre-pass)
     float *lse;            // [B,H,W] natural-log lse (saved for backward)
-    unsigned int *zdone;   // [B] zero shares of sample b completed
-    uint8_t *out;          // base of the output tensor (bytes)
-    long sample_bytes;     // H*W*C*esize
-    long share;            // zero share per item (bytes, multiple of 128)
-    int ahead;             // zero-ahead distance in samples (>= 1)
+    unsigned int *cdone;   // [B] producer items of sample b whose stores have completed (cleared by the statistics kernel)
+    int lag;               // item order: 1 = consumers trail the producers by one block, 0 = sample after sample
+    int hints;             // L2 eviction hints on the bulk copies
     long long *dbg;        // optional timeline buffer (CTA 0), -DCCA_TIMELINE builds only
 };
 
@@ -75,10 +75,9 @@ template <int LK, bool BF> struct FwdSmem {
     static constexpr int off_ld = 0;                          // kNLd load slots; every slot is the UMMA operand itself: a bf16 tile as
                                                               // loaded, an fp32 tile once the converters have rewritten it in place
     static constexpr int off_out = off_ld + kNLd * T::kSlot;  // kNOut staging slots
-    static constexpr int off_zero = off_out + kNOut * T::kSlot;   // zero tile.  (An M=128 MMA reads (128 - LK) rows past the end of
-                                                              // its Q slot: they land in the next slot / the staging slots and only
-                                                              // feed S rows >= LK, which are discarded.)
-    static constexpr int off_bar = off_zero + kZeroBuf;
+    // (An M=128 MMA reads (128 - LK) rows past the end of its Q slot: they land in the next slot / the staging slots and
+    // only feed S rows >= LK, which are discarded.)
+    static constexpr int off_bar = off_out + kNOut * T::kSlot + 1024;
     static constexpr int kBytes = off_bar + 8 * 40 + 32;
     static_assert(kBytes <= 232448, "shared memory budget");
 };
@@ -103,7 +102,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
     const int NCH = p.C / kNC;
     const int KQ = p.Cq / 16;                 // k-steps of the S MMA
     const int nk = p.sp.total > (int)blockIdx.x ? (p.sp.total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    auto item_of = [&](int k) { return decode_item(p.sp, (int)blockIdx.x + k * (int)gridDim.x); };
+    auto item_of = [&](int k) { return decode_item_order(p.sp, (int)blockIdx.x + k * (int)gridDim.x, p.lag); };
     // ring order:  Q0 K0 | V0[0..qkpos) Q1 K1 V0[qkpos..NCH) | V1[0..qkpos) Q2 K2 ...   (Q,K of the next item are slipped in
     // after the first chunks of the current one, so neither S(k+1) nor the first P V chunk of an item waits for the other)
     const int qkpos = NCH >= 3 ? 2 : NCH - 1;
@@ -120,10 +119,6 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
         prefetch_tmap(&mqc); prefetch_tmap(&mqr); prefetch_tmap(&mkc); prefetch_tmap(&mkr);
         prefetch_tmap(&mvc); prefetch_tmap(&mvr); prefetch_tmap(&moc); prefetch_tmap(&mor);
     }
-    if (tid < kZeroBuf / 16) {                                 // zero tile (read by the async proxy: fence before the barrier)
-        reinterpret_cast<uint4 *>(smem + S::off_zero)[tid] = make_uint4(0, 0, 0, 0);
-        fence_proxy_async();
-    }
     if (warp == 0) tmem_alloc<kTmemCols>(tmem_slot);
     tc_fence_before();
     __syncthreads();
@@ -138,6 +133,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                 uint32_t g = 0;
                 int dbg_n = 0;
                 (void)dbg_n;
+                const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
                 auto emit = [&](const CUtensorMap *mc, const CUtensorMap *mr, int c0, const Item &it, int start) {
                     const CUtensorMap *m = it.col ? mc : mr;
                     const int cw = it.col ? it.line : start, ch = it.col ? start : it.line;
@@ -146,8 +142,14 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                     CCA_STAMP(0);
                     uint8_t *dst = smem + S::off_ld + slot * T::kSlot;
                     mbar_expect_tx(&bars[B_LD_FULL + slot], T::kSlot);
-                    tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, it.b);
-                    if constexpr (!BF) tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, it.b);
+                    if (p.hints) {          // producers' operands are read again by the sample's consumers; theirs are not
+                        const uint64_t pol = is_producer(it) ? pol_keep : pol_stream;
+                        tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, it.b, pol);
+                        if constexpr (!BF) tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, it.b, pol);
+                    } else {
+                        tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, it.b);
+                        if constexpr (!BF) tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, it.b);
+                    }
                     ++g;
                 };
                 if (nk > 0) {
@@ -240,47 +242,48 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
         } else if (warp == kWarpStore) {
             // =============================== store warp (one lane) ===============================
             if (lane == 0) {
-                pdl_wait();                                // statistics kernel complete: counters and the head of `out` are cleared
-                int pending = -1;                          // sample whose zero share this lane has issued but not yet published
+                pdl_wait();                                // statistics kernel complete: the counters are cleared
+                const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+                const bool one_tile = p.sp.col.nt == 1 && p.sp.row.nt == 1;
                 for (int k = 0; k < nk; ++k) {
                     const Item it = item_of(k);
-                    const CUtensorMap *mo = it.col ? &moc : &mor;
+                    const bool prod = is_producer(it);
+                    const CUtensorMap *mo = it.col ? &moc : &mor;          // box = one tile of this direction, exactly
                     const int cw = it.col ? it.line : it.q0, ch = it.col ? it.q0 : it.line;
-                    const int zb = it.b + p.ahead;
-                    if (zb < p.sp.B) {                     // zero-ahead: this item's share of sample zb
-                        const long lo = (long)it.j * p.share;
-                        const long hi = lo + p.share < p.sample_bytes ? lo + p.share : p.sample_bytes;
-                        uint8_t *dst = p.out + (long)zb * p.sample_bytes;
-                        for (long o = lo; o < hi; o += kZeroBuf)
-                            bulk_store(dst + o, smem + S::off_zero, (uint32_t)(hi - o < kZeroBuf ? hi - o : kZeroBuf));
-                        tma_store_commit();
-                        pending = zb;
-                    }
                     for (int n = 0; n < NCH; ++n) {
                         const uint32_t c = (uint32_t)k * NCH + n;
                         const int os = c % kNOut;
                         mbar_wait(&bars[B_STAGED + os], (c / kNOut) & 1);
-                        if (n == 0) {
-                            if (pending >= 0) {            // the zero copies were issued a whole item-prologue ago: this wait is short
-                                tma_store_wait_all<0>();
-                                publish_count(p.zdone + pending);
-                                pending = -1;
-                            }
-                            if (it.b >= p.ahead) {         // every share of this sample's output has been cleared
-                                wait_count(p.zdone + it.b, (unsigned)p.sp.per_sample);
-                                fence_proxy_async_all();
-                            }
+                        if (n == 0 && !prod) {             // every producer of this sample has stored its tile
+                            wait_count(p.cdone + it.b, (unsigned)p.sp.seg0);
+                            fence_proxy_async_all();
                         }
                         const uint8_t *slot = smem + S::off_out + os * T::kSlot;
-                        tma_reduce_add_4d(mo, slot, n * kNC, cw, ch, it.b);
-                        if constexpr (!BF) tma_reduce_add_4d(mo, slot + T::kTile, n * kNC + 32, cw, ch, it.b);
+                        if (prod) {
+                            if (p.hints) {
+                                tma_store_4d(mo, slot, n * kNC, cw, ch, it.b, pol_keep);
+                                if constexpr (!BF) tma_store_4d(mo, slot + T::kTile, n * kNC + 32, cw, ch, it.b, pol_keep);
+                            } else {
+                                tma_store_4d(mo, slot, n * kNC, cw, ch, it.b);
+                                if constexpr (!BF) tma_store_4d(mo, slot + T::kTile, n * kNC + 32, cw, ch, it.b);
+                            }
+                        } else if (p.hints && one_tile) {  // the one and only add onto these lines: they are final
+                            tma_reduce_add_4d(mo, slot, n * kNC, cw, ch, it.b, pol_stream);
+                            if constexpr (!BF) tma_reduce_add_4d(mo, slot + T::kTile, n * kNC + 32, cw, ch, it.b, pol_stream);
+                        } else {
+                            tma_reduce_add_4d(mo, slot, n * kNC, cw, ch, it.b);
+                            if constexpr (!BF) tma_reduce_add_4d(mo, slot + T::kTile, n * kNC + 32, cw, ch, it.b);
+                        }
                         tma_store_commit();
                         tma_store_wait_read<0>();          // the tile has been read out of shared memory: hand the slot back
                         mbar_arrive(&bars[B_OUT_FREE + os]);
                     }
+                    if (prod) {                            // publish: the next chunk is a third of an item away, this wait is free
+                        tma_store_wait_all<0>();
+                        publish_count(p.cdone + it.b);
+                    }
                 }
                 tma_store_wait_all<0>();
-                if (pending >= 0) publish_count(p.zdone + pending);
             }
         }
     } else if (warp >= kWarpConv0) {
@@ -332,6 +335,11 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                 if (!it.col && it.ik == 0) p.lse[pix] = lse2 * kLn2;
             }
             const int self = it.col ? it.q0 + r - it.k0 : -1;          // masked key of this query (column branch only)
+            // The masks cost more ALU issue slots than the exponentials (ISETP/FSEL run at half rate): a 16-key chunk takes
+            // the predicated path only if it holds the tail of the key block or the self entry of one of this warp's 32
+            // query pixels -- a warp-uniform test; rows beyond the query tile get P = exp2(-inf) = 0 through their lse.
+            const int sw0 = it.col ? it.q0 - it.k0 + 32 * (warp & 3) : -(1 << 20);
+            const float nlse = rvalid ? -lse2 : -INFINITY;
             CCA_STAMP(3);
             mbar_wait(&bars[B_S_FULL], k & 1);
             mbar_wait(&bars[B_P_EMPTY + (k & 1)], ((k >> 1) & 1) ^ 1);    // P V of item k-2 has finished reading this buffer
@@ -345,15 +353,26 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                 tmem_ld16(tl + c0, reinterpret_cast<uint32_t *>(s));
                 tmem_ld_wait();
                 uint32_t hi[8], lo[8];
+                const bool masked = (c0 + 16 > it.lk) || (c0 + 16 > sw0 && c0 < sw0 + 32);
+                if (!masked) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int j = c0 + 2 * e;
-                    const bool ok0 = rvalid && j < it.lk && j != self;
-                    const bool ok1 = rvalid && j + 1 < it.lk && j + 1 != self;
-                    const float p0 = ok0 ? exp2f(s[2 * e] * kLog2e - lse2) : 0.f;
-                    const float p1 = ok1 ? exp2f(s[2 * e + 1] * kLog2e - lse2) : 0.f;
-                    if constexpr (BF) hi[e] = pack_bf16(p0, p1);
-                    else split2(p0, p1, hi[e], lo[e]);
+                    for (int e = 0; e < 8; ++e) {
+                        const float p0 = exp2f(fmaf(s[2 * e], kLog2e, nlse));
+                        const float p1 = exp2f(fmaf(s[2 * e + 1], kLog2e, nlse));
+                        if constexpr (BF) hi[e] = pack_bf16(p0, p1);
+                        else split2(p0, p1, hi[e], lo[e]);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int j = c0 + 2 * e;
+                        const bool ok0 = j < it.lk && j != self;
+                        const bool ok1 = j + 1 < it.lk && j + 1 != self;
+                        const float p0 = ok0 ? exp2f(fmaf(s[2 * e], kLog2e, nlse)) : 0.f;
+                        const float p1 = ok1 ? exp2f(fmaf(s[2 * e + 1], kLog2e, nlse)) : 0.f;
+                        if constexpr (BF) hi[e] = pack_bf16(p0, p1);
+                        else split2(p0, p1, hi[e], lo[e]);
+                    }
                 }
                 tmem_st8(pdst + c0 / 2, hi);
                 if constexpr (!BF) tmem_st8(pdst + LK / 2 + c0 / 2, lo);
@@ -419,27 +438,29 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
 long long *g_dbg = nullptr;   // timeline buffer (tools/tc_timeline.py, -DCCA_TIMELINE builds)
 
 template <int LK, bool BF>
-cudaError_t launch_fwd(const void *q, const void *k, const void *v, void *out, float *lse, const float *parts, unsigned int *zdone,
-                       Dims d, int ahead, cudaStream_t st, const char **why)
+cudaError_t launch_fwd(const void *q, const void *k, const void *v, void *out, float *lse, const float *parts, unsigned int *cdone,
+                       Dims d, cudaStream_t st, const char **why)
 {
     CUtensorMap m[8];
     const void *base[4] = {q, k, v, out};
     const int ch[4] = {d.Cq, d.Cq, d.C, d.C};
+    FwdParams p;
+    p.sp = make_space(d.B, d.H, d.W);
     for (int t = 0; t < 4; ++t)
-        for (int r = 0; r < 2; ++r)
-            if (!get_map(&m[2 * t + r], base[t], d.B, d.H, d.W, ch[t], LK, r == 0, BF)) {
+        for (int r = 0; r < 2; ++r) {
+            // loads: LK-pixel boxes (pixels past the image are zero-filled = the padding the MMAs need);
+            // output: boxes of exactly one tile of the direction, so a store never reaches into the next tile
+            const int rows = t < 3 ? LK : (r == 0 ? p.sp.col.tl : p.sp.row.tl);
+            if (!get_map(&m[2 * t + r], base[t], d.B, d.H, d.W, ch[t], rows, r == 0, BF)) {
                 if (why) *why = "cuTensorMapEncodeTiled failed";
                 return cudaErrorInvalidValue;
             }
-    FwdParams p;
-    p.sp = make_space(d.B, d.H, d.W);
+        }
     p.C = d.C; p.Cq = d.Cq;
     p.npix = (long)d.B * d.H * d.W;
-    p.parts = parts; p.lse = lse; p.zdone = zdone;
-    p.out = reinterpret_cast<uint8_t *>(out);
-    p.sample_bytes = (long)d.H * d.W * d.C * (BF ? 2 : 4);
-    p.share = zero_share_bytes(p.sample_bytes, p.sp.per_sample);
-    p.ahead = ahead;
+    p.parts = parts; p.lse = lse; p.cdone = cdone;
+    p.lag = tc_lag() != 0 ? 1 : 0;                 // default (-1): lagged
+    p.hints = tc_l2_hints();
     p.dbg = g_dbg;
     auto kern = cca_tc_fwd_kernel<LK, BF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem<LK, BF>::kBytes);
@@ -464,7 +485,7 @@ void set_tc_debug_buffer(void *p) { g_dbg = reinterpret_cast<long long *>(p); }
 
 bool tc_forward_supported(Dims d, int dtype) { return tc::shape_supported(d, dtype); }
 
-// Workspace of the forward: [nparts][B*H*W] fp32 partial lse planes, then [B] unsigned zero-ahead counters.
+// Workspace of the forward: [nparts][B*H*W] fp32 partial lse planes, then [B] unsigned per-sample counters.
 size_t tc_forward_workspace(Dims d)
 {
     const ItemSpace sp = make_space(d.B, d.H, d.W);
@@ -480,21 +501,17 @@ cudaError_t tc_forward(const void *q, const void *k, const void *v, void *out, f
     const long npix = (long)d.B * d.H * d.W;
     float *parts = reinterpret_cast<float *>(ws);
     const size_t parts_bytes = ((size_t)sp.nparts * npix * sizeof(float) + 15) & ~(size_t)15;
-    unsigned int *zdone = reinterpret_cast<unsigned int *>(reinterpret_cast<uint8_t *>(ws) + parts_bytes);
+    unsigned int *cdone = reinterpret_cast<unsigned int *>(reinterpret_cast<uint8_t *>(ws) + parts_bytes);
     const bool bf = dtype == CCA_BF16;
-    const long sample_bytes = (long)d.H * d.W * d.C * (bf ? 2 : 4);
-    int ahead = tc_zero_ahead();
-    if (ahead < 1) ahead = 1;
-    const int head = ahead < d.B ? ahead : d.B;
-    // statistics + clear the first `ahead` samples of out and the counters
-    cudaError_t e = tc_stats(q, k, parts, out, (long)head * sample_bytes, zdone, d.B, d, dtype, st, why);
+    // statistics; it also clears the per-sample counters of the values kernel
+    cudaError_t e = tc_stats(q, k, parts, nullptr, 0, cdone, d.B, d, dtype, st, why);
     if (e != cudaSuccess) return e;
     const int lk = lk_for(max_tile(sp));
     if (bf)
-        return lk == 80 ? launch_fwd<80, true>(q, k, v, out, lse, parts, zdone, d, ahead, st, why)
-                        : launch_fwd<112, true>(q, k, v, out, lse, parts, zdone, d, ahead, st, why);
-    return lk == 80 ? launch_fwd<80, false>(q, k, v, out, lse, parts, zdone, d, ahead, st, why)
-                    : launch_fwd<112, false>(q, k, v, out, lse, parts, zdone, d, ahead, st, why);
+        return lk == 80 ? launch_fwd<80, true>(q, k, v, out, lse, parts, cdone, d, st, why)
+                        : launch_fwd<112, true>(q, k, v, out, lse, parts, cdone, d, st, why);
+    return lk == 80 ? launch_fwd<80, false>(q, k, v, out, lse, parts, cdone, d, st, why)
+                    : launch_fwd<112, false>(q, k, v, out, lse, parts, cdone, d, st, why);
 }
 
 }  // namespace cca

@@ -14,8 +14,7 @@
 //   warps 8-15         fp32 only: fp32 -> bf16 hi/lo operand planes, in place (convert_slot_inplace)
 //   warp 17            MMA issuer: S = Q K^T (bf16x3 split for fp32 I/O), four S buffers in TMEM
 //   warps 0-3 / 4-7    two statistics groups (TMEM lane == query pixel), alternate items: row max, sum of exp2
-//   warps 18-19        clear the first samples of the forward's output and the per-sample counters of the values kernel
-//                      (its zero-ahead prologue; see cca_tc_fwd.cu)
+//   warps 18-19        clear the per-sample counters of the values kernel (and, if asked, a byte range)
 #include "cca_items.cuh"
 #include "cca_tc_common.cuh"
 
@@ -157,29 +156,45 @@ cca_tc_stats_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_consta
             tc_fence_after();
             const uint32_t ts = tl + (k % kNSB) * 128;
             const int self = it.col ? it.q0 + r - it.k0 : -1;      // masked key of this query (column branch only)
-            float m = -INFINITY;
+            // predicated path only for the 16-key chunks that hold the tail of the key block or the self entry of one of this
+            // warp's 32 query pixels (warp-uniform test): the masks cost more ALU issue slots than the arithmetic
+            const int sw0 = it.col ? it.q0 - it.k0 + 32 * (warp & 3) : -(1 << 20);
+            float m = -INFINITY;                                   // row max of the raw logits (log2e > 0: scale afterwards)
 #pragma unroll 1
-            for (int c0 = 0; c0 < LK; c0 += 16) {
+            for (int c0 = 0; c0 < it.lk; c0 += 16) {
                 float s[16];
                 tmem_ld16(ts + c0, reinterpret_cast<uint32_t *>(s));
                 tmem_ld_wait();
+                const bool masked = (c0 + 16 > it.lk) || (c0 + 16 > sw0 && c0 < sw0 + 32);
+                if (!masked) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const int j = c0 + e;
-                    m = fmaxf(m, (j < it.lk && j != self) ? s[e] * kLog2e : -INFINITY);
+                    for (int e = 0; e < 16; ++e) m = fmaxf(m, s[e]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int j = c0 + e;
+                        m = fmaxf(m, (j < it.lk && j != self) ? s[e] : -INFINITY);
+                    }
                 }
             }
+            m *= kLog2e;
             const float msub = (m == -INFINITY) ? 0.f : m;
             float l = 0.f;
 #pragma unroll 1
-            for (int c0 = 0; c0 < LK; c0 += 16) {
+            for (int c0 = 0; c0 < it.lk; c0 += 16) {
                 float s[16];
                 tmem_ld16(ts + c0, reinterpret_cast<uint32_t *>(s));
                 tmem_ld_wait();
+                const bool masked = (c0 + 16 > it.lk) || (c0 + 16 > sw0 && c0 < sw0 + 32);
+                if (!masked) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const int j = c0 + e;
-                    l += (j < it.lk && j != self) ? exp2f(s[e] * kLog2e - msub) : 0.f;
+                    for (int e = 0; e < 16; ++e) l += exp2f(fmaf(s[e], kLog2e, -msub));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int j = c0 + e;
+                        l += (j < it.lk && j != self) ? exp2f(fmaf(s[e], kLog2e, -msub)) : 0.f;
+                    }
                 }
             }
             tc_fence_before();

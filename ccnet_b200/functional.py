@@ -120,6 +120,81 @@ def cca_backward(dout, q, k, v, out, lse, impl: str = "auto"):
     return dq, dk, dv
 
 
+def qkv_gemm_eligible(x: torch.Tensor, Cq: int) -> bool:
+    """True if the hand-written tcgen05 projection GEMMs cover x [B,C,H,W] (fp32, C and Cq multiples of 64)."""
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+            and capi.load().cca_b200_qkv_supported(x.shape[1], Cq) == 1)
+
+
+def _as_matrix_ptr(t: torch.Tensor) -> int:
+    if not t.is_contiguous(memory_format=torch.channels_last) and not (t.dim() == 2 and t.is_contiguous()):
+        raise RuntimeError("ccnet_b200: projection GEMMs need channels-last activations")
+    return t.data_ptr()
+
+
+def qkv_project(x, wq, bq, wk, bk, wv, bv):
+    """q, k, v = the three 1x1 convs of cc_attention/functions.py:29,32,35 applied to channels-last x, as ONE tcgen05 GEMM
+    launch emitting channels-last q, k, v.  fp32, C % 64 == 0, Cq % 64 == 0 (``qkv_gemm_eligible``)."""
+    lib = capi.load()
+    B, C, H, W = x.shape
+    Cq = wq.shape[0]
+    x = x.contiguous(memory_format=torch.channels_last)
+    ws_w = [w.contiguous() for w in (wq, wk, wv)]
+    bs = [b.contiguous() for b in (bq, bk, bv)]
+    with torch.cuda.device(x.device):
+        q = torch.empty((B, Cq, H, W), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        k = torch.empty_like(q, memory_format=torch.channels_last)
+        v = torch.empty((B, C, H, W), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        nws = lib.cca_b200_qkv_workspace_bytes(C, Cq)
+        ws = torch.empty((nws,), dtype=torch.uint8, device=x.device)
+        rc = lib.cca_b200_qkv_project(_as_matrix_ptr(x), ws_w[0].data_ptr(), bs[0].data_ptr(), ws_w[1].data_ptr(), bs[1].data_ptr(),
+                                      ws_w[2].data_ptr(), bs[2].data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(),
+                                      ws.data_ptr(), ws.numel(), B * H * W, C, Cq, _stream_ptr(x.device))
+    capi.check(rc, "cca_b200_qkv_project")
+    return q, k, v
+
+
+def qkv_project_dgrad(dq, dk, dv, wq, wk, wv, scale=None):
+    """dx = s (dq Wq + dk Wk + dv Wv) (input gradient of the three projections), channels-last fp32, one tcgen05 GEMM launch.
+    ``scale``: optional one-element CUDA tensor s (the residual's gamma), folded into the packed weights."""
+    lib = capi.load()
+    B, C, H, W = dv.shape
+    Cq = dq.shape[1]
+    dq, dk, dv = (t.contiguous(memory_format=torch.channels_last) for t in (dq, dk, dv))
+    ws_w = [w.contiguous() for w in (wq, wk, wv)]
+    with torch.cuda.device(dv.device):
+        dx = torch.empty_like(dv, memory_format=torch.channels_last)
+        nws = lib.cca_b200_qkv_workspace_bytes(C, Cq)
+        ws = torch.empty((nws,), dtype=torch.uint8, device=dv.device)
+        rc = lib.cca_b200_qkv_project_dgrad(dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), ws_w[0].data_ptr(), ws_w[1].data_ptr(),
+                                            ws_w[2].data_ptr(), scale.data_ptr() if scale is not None else None, dx.data_ptr(),
+                                            ws.data_ptr(), ws.numel(), B * H * W, C, Cq, 0, _stream_ptr(dv.device))
+    capi.check(rc, "cca_b200_qkv_project_dgrad")
+    return dx
+
+
+def qkv_wgrad_eligible(C: int, Cq: int) -> bool:
+    return capi.load().cca_b200_qkv_wgrad_supported(C, Cq) == 1
+
+
+def qkv_project_wgrad(x, dq, dk, dv, scale=None):
+    """(dWq, dbq, dWk, dbk, dWv, dbv) = s * (gradients of the three 1x1 convs' parameters), one split-K tcgen05 launch."""
+    lib = capi.load()
+    B, C, H, W = x.shape
+    Cq = dq.shape[1]
+    x, dq, dk, dv = (t.contiguous(memory_format=torch.channels_last) for t in (x, dq, dk, dv))
+    with torch.cuda.device(x.device):
+        dwq = torch.empty((Cq, C), dtype=x.dtype, device=x.device)
+        dwk = torch.empty((Cq, C), dtype=x.dtype, device=x.device)
+        dwv = torch.empty((C, C), dtype=x.dtype, device=x.device)
+        db = torch.empty((2 * Cq + C,), dtype=x.dtype, device=x.device)
+        rc = lib.cca_b200_qkv_project_wgrad(x.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                            scale.data_ptr() if scale is not None else None, dwq.data_ptr(), dwk.data_ptr(),
+                                            dwv.data_ptr(), db.data_ptr(), B * H * W, C, Cq, _stream_ptr(x.device))
+    capi.check(rc, "cca_b200_qkv_project_wgrad")
+    return dwq, db[:Cq], dwk, db[Cq:2 * Cq], dwv, db[2 * Cq:]
+
+
 class _CCAFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, impl):

@@ -91,9 +91,10 @@ CCA_API int cca_b200_tc_supported(int which, int B, int Cq, int C, int H, int W,
 /* Introspection of the tensor-core kernels' work decomposition (host-only, no CUDA call; see csrc/cca_items.cuh):
  * item_space: out8 = {total items, items per sample, column/first-key-block items, other column items, row items,
  *                     tiles per column line, tiles per row line, padded tile length (80 or 112; 0 = not covered)}
- * decode_item: out10 = {is_column, sample, line, query tile, key block, q0, lq, k0, lk, index inside the sample}. */
+ * decode_item: out10 = {is_column, sample, line, query tile, key block, q0, lq, k0, lk, index inside the sample};
+ *   lagged = 0: samples one after the other; 1: the consumers of a sample trail its producers by one block. */
 CCA_API void cca_b200_item_space(int B, int H, int W, int *out8);
-CCA_API void cca_b200_decode_item(int B, int H, int W, int index, int *out10);
+CCA_API void cca_b200_decode_item(int B, int H, int W, int index, int lagged, int *out10);
 
 /* Bytes of device workspace the forward / backward call needs for this problem. */
 CCA_API size_t cca_b200_workspace_bytes(int which, int B, int Cq, int C, int H, int W, int dtype);
@@ -119,6 +120,31 @@ CCA_API int cca_b200_backward(const void *dout, const void *q, const void *k, co
                       void *workspace, size_t workspace_bytes,
                       int B, int Cq, int C, int H, int W, int dtype, unsigned flags,
                       void *cuda_stream);
+
+/*
+ * The three 1x1 projections in front of the step (replace functions.py:29,32,35 -- query_conv, key_conv, value_conv -- and
+ * their input gradient) as hand-written tcgen05 GEMMs on the channels-last view: x, v, dx are [pixels, C], q, k, dq, dk are
+ * [pixels, Cq] row-major fp32 (a channels-last [B,C,H,W] tensor IS that matrix with pixels = B*H*W); weights are the conv
+ * weights [out, in] row-major ([out,in,1,1] contiguous).  fp32 accuracy via the bf16 hi/lo split (3 MMAs per product).
+ *   qkv_project       : q = x Wq^T + bq,  k = x Wk^T + bk,  v = x Wv^T + bv
+ *   qkv_project_dgrad : dx (+)= s (dq Wq + dk Wk + dv Wv)    (accumulate != 0 adds onto dx)
+ *   qkv_project_wgrad : dWq = s dq^T x, dWk = s dk^T x, dWv = s dv^T x  and  db = s [sum_p dq | sum_p dk | sum_p dv]
+ *                       (db: 2 Cq + C floats in that order, may be NULL; outputs are cleared by the call)
+ * `scale` (s) is a DEVICE pointer to one float or NULL (= 1): the gamma of functions.py:49, applied to the small matrices
+ * instead of to the [pixels, C] gradient.  Covered: C % 64 == 0, Cq % 64 == 0, 2 Cq + C <= 1024 (wgrad: C % 256 == 0).
+ */
+CCA_API int cca_b200_qkv_supported(int C, int Cq);
+CCA_API size_t cca_b200_qkv_workspace_bytes(int C, int Cq);
+CCA_API int cca_b200_qkv_project(const float *x, const float *wq, const float *bq, const float *wk, const float *bk,
+                                 const float *wv, const float *bv, float *q, float *k, float *v,
+                                 void *workspace, size_t workspace_bytes, long long pixels, int C, int Cq, void *cuda_stream);
+CCA_API int cca_b200_qkv_project_dgrad(const float *dq, const float *dk, const float *dv, const float *wq, const float *wk,
+                                       const float *wv, const float *scale, float *dx, void *workspace, size_t workspace_bytes,
+                                       long long pixels, int C, int Cq, int accumulate, void *cuda_stream);
+CCA_API int cca_b200_qkv_wgrad_supported(int C, int Cq);
+CCA_API int cca_b200_qkv_project_wgrad(const float *x, const float *dq, const float *dk, const float *dv, const float *scale,
+                                       float *dwq, float *dwk, float *dwv, float *db,
+                                       long long pixels, int C, int Cq, void *cuda_stream);
 
 /*
  * Host-buffer variants: same maths, pointers are HOST memory (pinned or pageable).

@@ -73,6 +73,8 @@ def test_forward_fp32_vs_oracle(shape, impl):
 TC_SHAPES = [
     (2, 32, 256, 20, 97), (1, 64, 64, 112, 80), (3, 16, 64, 1, 5), (2, 16, 64, 5, 1), (1, 48, 192, 81, 112),
     (1, 16, 128, 1, 1), (2, 64, 512, 33, 47), (8, 64, 512, 97, 97),
+    # lines longer than one tile (key-block tiling, cca_items.cuh): BASELINE configs[4] sweep points and ragged ones
+    (1, 64, 512, 129, 129), (1, 64, 512, 193, 193), (1, 32, 128, 113, 200), (2, 16, 64, 230, 7), (1, 16, 64, 1, 300),
 ]
 
 
@@ -88,7 +90,7 @@ def test_forward_tensor_core_vs_oracle_and_simt(shape):
     assert out.shape == v.shape and out.is_contiguous(memory_format=torch.channels_last)
     so, sl = cca_forward(qd, kd, vd, impl="simt")
     assert (out - so).abs().max().item() <= 5e-4 and (lse - sl).abs().max().item() <= 5e-4
-    if shape[0] * shape[3] * shape[4] <= 4 * 97 * 97:
+    if shape[0] * shape[3] * shape[4] <= 4 * 97 * 97 or shape[0] == 1:
         ro, rl = O.cca_forward(q.double(), k.double(), v.double())
         assert (out.cpu().double() - ro).abs().max().item() <= 5e-4
         assert (lse.cpu().double() - rl).abs().max().item() <= 5e-4
@@ -98,7 +100,8 @@ def test_forward_tensor_core_vs_oracle_and_simt(shape):
 
 
 @pytest.mark.parametrize("shape", [(2, 32, 256, 20, 97), (1, 64, 64, 112, 80), (3, 16, 64, 1, 5), (2, 16, 64, 5, 1),
-                                   (1, 48, 192, 81, 112), (1, 16, 128, 1, 1), (2, 64, 512, 33, 47), (1, 64, 512, 97, 97)])
+                                   (1, 48, 192, 81, 112), (1, 16, 128, 1, 1), (2, 64, 512, 33, 47), (1, 64, 512, 97, 97),
+                                   (1, 64, 512, 129, 129), (1, 64, 512, 193, 193), (1, 32, 128, 113, 200), (2, 16, 64, 230, 7)])
 def test_backward_tensor_core_vs_oracle(shape):
     """tcgen05 backward (channels-last, bf16x3 split, P recomputed from lse) against the fp64 closed form."""
     from ccnet_b200 import cca_backward, cca_forward
@@ -121,10 +124,11 @@ def test_backward_tensor_core_vs_oracle(shape):
         assert (got - ref).abs().max().item() <= FP32_TOL * max(1.0, ref.abs().max().item())
 
 
-@pytest.mark.parametrize("shape", [(2, 32, 256, 20, 97), (1, 64, 64, 112, 80), (3, 16, 64, 1, 5), (2, 64, 512, 33, 47), (2, 64, 512, 97, 97)])
+@pytest.mark.parametrize("shape", [(2, 32, 256, 20, 97), (1, 64, 64, 112, 80), (3, 16, 64, 1, 5), (2, 64, 512, 33, 47), (2, 64, 512, 97, 97),
+                                   (1, 64, 512, 129, 129), (1, 64, 512, 193, 193), (1, 32, 128, 113, 200)])
 def test_bf16_tensor_core_forward_backward_vs_oracle(shape):
     """bf16 I/O on the tcgen05 kernels (single-term MMAs, bf16 staging / TMA reduce-add): against the fp64 oracle
-    evaluated on the bf16-rounded inputs, tolerance 1e-2 (forward) / 3e-2 (gradients), relative to max|ref|."""
+    evaluated on the bf16-rounded inputs, tolerance 1e-2 relative to max|ref| (north_star), forward and gradients."""
     from ccnet_b200 import cca_backward, cca_forward
     O = _oracle()
     dev = _dev()
@@ -141,73 +145,84 @@ def test_bf16_tensor_core_forward_backward_vs_oracle(shape):
     for got, ref, name in ((dq, rq, "dq"), (dk, rk, "dk"), (dv, rv, "dv")):
         assert got.dtype == torch.bfloat16
         err = (got.cpu().double() - ref).abs().max().item()
-        assert err <= 3 * BF16_TOL * max(1.0, ref.abs().max().item()), (name, err)
+        assert err <= BF16_TOL * max(1.0, ref.abs().max().item()), (name, err)
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("CCA_TEST_FUSED"), reason="experimental single-launch modes (set CCA_TEST_FUSED=1)")
-def test_forward_fused_launch_matches_two_launch_mode():
-    """EXPERIMENTAL single-launch modes (dynamic scheduling / static interleaved order with per-sample completion counters)
-    against the default two-launch mode: results must be bit-identical.  Off by default: the modes are not faster yet and
-    an intermittent failure was seen once on B200."""
-    import ctypes
-    from ccnet_b200 import capi, cca_forward
-    dev = _dev()
-    lib = capi.load()
-    hook = lib.cca_b200__set_two_pass
-    hook.argtypes = [ctypes.c_int]
-    hook.restype = None
-    for shape in [(8, 64, 512, 97, 97), (3, 32, 128, 40, 77), (1, 16, 64, 9, 5)]:
-        q, k, v = _rand_qkv(*shape, seed=31 + sum(shape))
-        qd, kd, vd = q.to(dev), k.to(dev), v.to(dev)
-        try:
-            hook(1)                                   # two launches
-            ref_o, ref_l = cca_forward(qd, kd, vd, impl="tc")
-            for mode in (0, 2):                       # one launch: dynamic scheduling / static interleaved order
-                hook(mode)
-                for _ in range(4):
-                    o, l = cca_forward(qd, kd, vd, impl="tc")
-                    assert torch.equal(o, ref_o) and torch.equal(l, ref_l)
-        finally:
-            hook(1)
+def _debug_hook(lib, name, argtypes):
+    """A/B hooks exist in debug builds only (python -m ccnet_b200.build --debug)."""
+    try:
+        fn = getattr(lib, name)
+    except AttributeError:
+        return None
+    fn.argtypes, fn.restype = argtypes, None
+    return fn
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 def test_launch_knobs_are_bit_identical(dtype):
-    """Programmatic dependent launch (off / on / overlapped second pass) and the L2 eviction hints only change WHEN and
-    WHERE bytes move, never the arithmetic: forward and backward must be bit-identical to the plain serial launches.
-    Repeated a few times at the BASELINE shape (all 148 CTAs busy) to give an ordering bug a chance to show."""
+    """Programmatic dependent launch (off / on), the item order (lagged or not), the L2 eviction hints and the backward's delta
+    mode only change WHEN and WHERE bytes move, never the arithmetic: with one tile per line every output element is one
+    store plus one add, so forward and backward must be bit-identical across knobs and repetitions.
+    Repeated at the BASELINE shape (all 148 CTAs busy) to give an ordering bug a chance to show."""
     import ctypes
     from ccnet_b200 import capi, cca_backward, cca_forward
     dev = _dev()
     lib = capi.load()
-    pdl = lib.cca_b200__set_pdl
-    pdl.argtypes = [ctypes.c_int]
-    pdl.restype = None
-    hint = lib.cca_b200__set_l2_hints
-    hint.argtypes = [ctypes.c_int, ctypes.c_double]
-    hint.restype = None
+    pdl = _debug_hook(lib, "cca_b200__set_pdl", [ctypes.c_int])
+    ahead = _debug_hook(lib, "cca_b200__set_zero_ahead", [ctypes.c_int])
+    dmode = _debug_hook(lib, "cca_b200__set_delta_mode", [ctypes.c_int])
+    lag = _debug_hook(lib, "cca_b200__set_lag", [ctypes.c_int])
+    hint = _debug_hook(lib, "cca_b200__set_l2_hints", [ctypes.c_int])
     dt = torch.float32 if dtype == "fp32" else torch.bfloat16
     cl = torch.channels_last
-    for shape in [(8, 64, 512, 97, 97), (2, 32, 256, 20, 97)]:
+    # (pdl, delta mode, lag, hints)
+    combos = [(1, -1, -1, 1)] if pdl is None else [(1, -1, -1, 1), (0, -1, -1, 1), (1, 0, 0, 1), (1, 1, 1, 0), (0, 0, 1, 1), (1, 1, 0, 0)]
+    for shape in [(8, 64, 512, 97, 97), (2, 32, 256, 20, 97), (5, 16, 64, 7, 3)]:
         q, k, v = _rand_qkv(*shape, seed=5 + sum(shape))
         q, k, v = (t.to(dev).to(dt).contiguous(memory_format=cl) for t in (q, k, v))
         do = torch.randn(v.shape, device=dev).to(dt).contiguous(memory_format=cl)
+        ro = rl = rg = None
         try:
-            pdl(0)
-            hint(0, 80.0)
-            ro, rl = cca_forward(q, k, v, impl="tc")
-            rg = cca_backward(do, q, k, v, ro, rl, impl="tc")
-            for level, hints in ((1, 0), (2, 0), (1, 1), (0, 1)):
-                pdl(level)
-                hint(hints, 80.0)
+            for (lv, dm, lg, hn) in combos:
+                if pdl is not None:
+                    pdl(lv); dmode(dm); lag(lg); hint(hn)
                 for _ in range(4):
                     o, l = cca_forward(q, k, v, impl="tc")
                     g = cca_backward(do, q, k, v, o, l, impl="tc")
-                    assert torch.equal(o, ro) and torch.equal(l, rl), (shape, level, hints)
-                    assert all(torch.equal(a, b) for a, b in zip(g, rg)), (shape, level, hints)
+                    if ro is None:
+                        ro, rl, rg = o, l, g
+                    assert torch.equal(o, ro) and torch.equal(l, rl), (shape, lv, dm, lg, hn)
+                    # delta computed per item or fetched from the producers is the same number either way
+                    assert all(torch.equal(a, b) for a, b in zip(g, rg)), (shape, lv, dm, lg, hn)
         finally:
-            pdl(1)
-            hint(0, 80.0)
+            if pdl is not None:
+                pdl(1); dmode(-1); lag(-1); hint(1)
+
+
+@pytest.mark.parametrize("dtype,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_backward_full_batch_c2_vs_oracle(dtype, tol):
+    """BASELINE config 2 (B=8, C=512, 97x97): forward AND backward of the persistent single-launch schedule (776 lines per
+    direction over 148 CTAs, zero-ahead and delta hand-off between CTAs) against the fp64 oracle on the first, a middle and
+    the last sample."""
+    from ccnet_b200 import cca_backward, cca_forward
+    O = _oracle()
+    dev = _dev()
+    dt = torch.float32 if dtype == "fp32" else torch.bfloat16
+    shape = (8, 64, 512, 97, 97)
+    q, k, v = _rand_qkv(*shape, seed=1234, scale=0.6, dtype=dt)
+    dout = torch.randn(v.shape, generator=torch.Generator().manual_seed(8)).to(dt)
+    qd, kd, vd, dd = q.to(dev), k.to(dev), v.to(dev), dout.to(dev)
+    out, lse = cca_forward(qd, kd, vd, impl="tc")
+    dq, dk, dv = cca_backward(dd, qd, kd, vd, out, lse, impl="tc")
+    for b in (0, 3, 7):
+        sl = slice(b, b + 1)
+        ro, rl = O.cca_forward(q[sl].double(), k[sl].double(), v[sl].double())
+        rq, rk, rv = O.cca_backward(dout[sl].double(), q[sl].double(), k[sl].double(), v[sl].double())
+        assert (out[sl].cpu().double() - ro).abs().max().item() <= tol * max(1.0, ro.abs().max().item()), b
+        assert (lse[sl].cpu().double() - rl).abs().max().item() <= tol, b
+        for got, ref, name in ((dq, rq, "dq"), (dk, rk, "dk"), (dv, rv, "dv")):
+            err = (got[sl].cpu().double() - ref).abs().max().item()
+            assert err <= tol * max(1.0, ref.abs().max().item()), (b, name, err)
 
 
 def test_tensor_core_peaky_softmax_stress():
@@ -371,3 +386,71 @@ def test_noncontiguous_inputs_and_fresh_output():
     ro, _ = O.cca_forward(q.double(), k.double(), v.double())
     assert (out.cpu().double() - ro).abs().max().item() <= FP32_TOL
     assert out.data_ptr() != vd.data_ptr()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# hand-written projection GEMMs (functions.py:29,32,35) and the fused module step around the operator
+# ---------------------------------------------------------------------------------------------------------------------
+def _proj_params(C, seed):
+    g = torch.Generator().manual_seed(seed)
+    Cq = C // 8
+    bound = 1.0 / (C ** 0.5)
+    mk = lambda *s: (torch.rand(*s, generator=g) * 2 - 1) * bound
+    return mk(Cq, C), mk(Cq), mk(Cq, C), mk(Cq), mk(C, C), mk(C)
+
+
+@pytest.mark.parametrize("shape", [(1, 512, 97, 97), (3, 512, 20, 31), (1, 512, 1, 5)])
+def test_qkv_projection_gemm_vs_fp64(shape):
+    """tcgen05 bf16x3 GEMM of the three 1x1 convs against fp64 matmul: fp32-level accuracy (north_star 1e-3, typical 1e-5)."""
+    from ccnet_b200.functional import qkv_gemm_eligible, qkv_project, qkv_project_dgrad
+    dev = _dev()
+    B, C, H, W = shape
+    wq, bq, wk, bk, wv, bv = _proj_params(C, 5)
+    x = torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(1))
+    xd = x.to(dev).contiguous(memory_format=torch.channels_last)
+    assert qkv_gemm_eligible(xd, C // 8)
+    q, k, v = qkv_project(xd, wq.to(dev), bq.to(dev), wk.to(dev), bk.to(dev), wv.to(dev), bv.to(dev))
+    xm = x.double().permute(0, 2, 3, 1).reshape(-1, C)
+    for got, w, b in ((q, wq, bq), (k, wk, bk), (v, wv, bv)):
+        ref = xm @ w.double().t() + b.double()
+        assert got.is_contiguous(memory_format=torch.channels_last) and got.shape[1] == w.shape[0]
+        err = (got.cpu().double().permute(0, 2, 3, 1).reshape(-1, w.shape[0]) - ref).abs().max().item()
+        assert err <= 1e-4 * max(1.0, ref.abs().max().item()), err
+    # input gradient
+    gq, gk, gv = (torch.randn(t.shape, generator=torch.Generator().manual_seed(7 + i)) for i, t in enumerate((q, k, v)))
+    dx = qkv_project_dgrad(*(g.to(dev).contiguous(memory_format=torch.channels_last) for g in (gq, gk, gv)),
+                           wq.to(dev), wk.to(dev), wv.to(dev))
+    ref = sum(g.double().permute(0, 2, 3, 1).reshape(-1, w.shape[0]) @ w.double() for g, w in ((gq, wq), (gk, wk), (gv, wv)))
+    err = (dx.cpu().double().permute(0, 2, 3, 1).reshape(-1, C) - ref).abs().max().item()
+    assert err <= 1e-4 * max(1.0, ref.abs().max().item()), err
+
+
+def test_fused_module_step_c512_vs_oracle_module():
+    """The user-facing module at C=512 (every kernel of the step is this repo's: projection GEMMs, attention, backward) against
+    the oracle module on the CPU, recurrence 2, all seven parameter gradients."""
+    import cc_attention
+    from ccnet_b200.module import _FusedCCAStep  # noqa: F401  (the path under test)
+    O = _oracle()
+    dev = _dev()
+    torch.manual_seed(3)
+    C, H, W = 512, 24, 40
+    ref = O.CrissCrossAttentionOracle(C)
+    with torch.no_grad():
+        ref.gamma.fill_(0.7)
+    m = cc_attention.CrissCrossAttention(C).to(dev)
+    m.load_state_dict(ref.state_dict())
+    x = torch.randn(2, C, H, W)
+    g = torch.randn(2, C, H, W)
+    xd = x.to(dev).requires_grad_(True)
+    y = m(m(xd))
+    (y * g.to(dev)).sum().backward()
+    xr = x.clone().requires_grad_(True)
+    yr = ref(ref(xr))
+    (yr * g).sum().backward()
+    assert (y.detach().cpu() - yr.detach()).abs().max().item() <= FP32_TOL
+    assert (xd.grad.cpu() - xr.grad).abs().max().item() <= FP32_TOL * max(1.0, xr.grad.abs().max().item())
+    rp = dict(ref.named_parameters())
+    for n, p in m.named_parameters():
+        r = rp[n].grad
+        scale = rp[n.replace(".bias", ".weight")].grad.abs().max().item() if n.endswith(".bias") else r.abs().max().item()
+        assert (p.grad.cpu() - r).abs().max().item() <= 2e-3 * max(1.0, scale), n

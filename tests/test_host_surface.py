@@ -27,9 +27,9 @@ def test_version_and_workspace_and_strerror_without_gpu():
     lib = capi.load()
     assert lib.cca_b200_version() == 200
     px = 8 * 97 * 97
-    # forward: two partial-lse planes (row + column) + 8 zero-ahead counters; backward: delta + 2 x 8 counters
+    # forward: two partial-lse planes (row + column) + 8 zero-ahead counters; backward: delta + 3 x 8 counters
     assert lib.cca_b200_workspace_bytes(capi.CCA_WS_FORWARD, 8, 64, 512, 97, 97, capi.CCA_F32) == px * 8 + 32
-    assert lib.cca_b200_workspace_bytes(capi.CCA_WS_BACKWARD, 8, 64, 512, 97, 97, capi.CCA_F32) == px * 4 + 64
+    assert lib.cca_b200_workspace_bytes(capi.CCA_WS_BACKWARD, 8, 64, 512, 97, 97, capi.CCA_F32) == px * 4 + 96
     # lines longer than 112 pixels are tiled: one plane per key block
     assert lib.cca_b200_workspace_bytes(capi.CCA_WS_FORWARD, 1, 64, 512, 193, 193, capi.CCA_F32) == 193 * 193 * 16 + 16
     assert lib.cca_b200_tc_supported(capi.CCA_WS_FORWARD, 1, 8, 64, 32, 32, capi.CCA_F32) == 0      # Cq < 16

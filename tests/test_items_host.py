@@ -18,9 +18,9 @@ def _space(B, H, W):
     return dict(zip(("total", "per_sample", "seg0", "seg1", "seg2", "ntc", "ntr", "lk"), list(out)))
 
 
-def _item(B, H, W, idx):
+def _item(B, H, W, idx, lagged=0):
     out = (ctypes.c_int * 10)()
-    capi.load().cca_b200_decode_item(B, H, W, idx, out)
+    capi.load().cca_b200_decode_item(B, H, W, idx, lagged, out)
     return dict(zip(("col", "b", "line", "iq", "ik", "q0", "lq", "k0", "lk", "j"), list(out)))
 
 
@@ -81,3 +81,26 @@ def test_zero_shares_tile_the_sample():
                 assert lo == covered and (hi - lo) % 16 == 0
                 covered = hi
         assert covered == sample
+
+
+@pytest.mark.parametrize("shape", [(1, 5, 6), (3, 5, 6), (8, 97, 97), (2, 129, 129), (4, 1, 300)])
+def test_lagged_order_is_a_dependency_safe_permutation(shape):
+    """decode_item_lagged: same items as the plain order; every producer (column, first key block) of a sample comes before
+    every consumer of that sample (consumers only ever wait for lower indices), and the consumers of sample b come after
+    the producers of sample b+1 (the one-block lag)."""
+    B, H, W = shape
+    sp = _space(B, H, W)
+    key = lambda it: (it["b"], it["j"])
+    plain = sorted(key(_item(B, H, W, i)) for i in range(sp["total"]))
+    lag = [_item(B, H, W, i, 1) for i in range(sp["total"])]
+    assert sorted(key(it) for it in lag) == plain
+    last_prod, first_cons = {}, {}
+    for i, it in enumerate(lag):
+        if it["col"] and it["ik"] == 0:
+            last_prod[it["b"]] = i
+        else:
+            first_cons.setdefault(it["b"], i)
+    for b in range(B):
+        assert last_prod[b] < first_cons[b]
+        if b + 1 < B:
+            assert last_prod[b + 1] < first_cons[b]

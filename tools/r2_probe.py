@@ -27,7 +27,7 @@ def main():
     do = torch.randn(B, C, H, W, generator=g).to(dt)
     cl = torch.channels_last
     qd, kd, vd, dd = (t.to(dev).contiguous(memory_format=cl) for t in (q, k, v, do))
-    knobs = {n: os.environ.get(n) for n in ("CCA_B200_PDL", "CCA_B200_ZERO_AHEAD", "CCA_B200_DELTA") if os.environ.get(n)}
+    knobs = {n: os.environ.get(n) for n in ("CCA_B200_PDL", "CCA_B200_ZERO_AHEAD", "CCA_B200_DELTA", "CCA_B200_LAG", "CCA_B200_L2HINT") if os.environ.get(n)}
     rec = {"mode": mode, "shape": [B, Cq, C, H, W], "dtype": sys.argv[7], "knobs": knobs}
     if mode == "parity":
         from oracle import cca_oracle as O
