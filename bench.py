@@ -465,6 +465,21 @@ def run_ours(args):
         del q2, k2, v2, do2, out2, lse2
     roofline["other_dtype"] = other
 
+    # ---- the network around the operator (BASELINE configs[2], [3]): ResNet101+RCCA, synthetic 769x769, global batch 8 ----
+    ccnet = None
+    if not args.no_train:
+        del x, g, x_dev, y_dev, dx_dev, q, k, v, do, out, lse, flush
+        torch.cuda.empty_cache()
+        from harness.train_synth import run as train_run
+        try:
+            ccnet = train_run(local_rank, world, steps=max(2, min(args.steps, 4)), warmup=2, allow_tf32=True)
+            ccnet["note"] = ("train step = the reference's loop (train.py:199-239) on synthetic data, stock torch backbone (cudnn, TF32 "
+                             "convolutions = torch default), DDP + SyncBatchNorm when N > 1, per-GPU batch = 8 / N (engine.py:88); "
+                             "cca_modules_ms = the R criss-cross modules alone (projection GEMMs + operator + residual, fwd+bwd) "
+                             "at the head's feature-map size")
+        except Exception as exc:                      # never lose the main line to the extra leg
+            ccnet = {"error": repr(exc)[:300]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         r = cpu_reference_run(3, 1)
@@ -482,7 +497,7 @@ def run_ours(args):
                            "parallelism": f"dp{world} (image-sharded, DDP grad all-reduce only)",
                            "host_binding": numa},
                 "clocks": clk.summary(), "e2e": e2e, "module": module, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu}
+                "roofline": roofline, "ccnet": ccnet, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -497,6 +512,7 @@ def main():
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--kernels", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-train", action="store_true", help="skip the ResNet101+RCCA train-step leg (BASELINE configs[2], [3])")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     if args.impl == "reference":

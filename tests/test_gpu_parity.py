@@ -423,6 +423,18 @@ def test_qkv_projection_gemm_vs_fp64(shape):
     ref = sum(g.double().permute(0, 2, 3, 1).reshape(-1, w.shape[0]) @ w.double() for g, w in ((gq, wq), (gk, wk), (gv, wv)))
     err = (dx.cpu().double().permute(0, 2, 3, 1).reshape(-1, C) - ref).abs().max().item()
     assert err <= 1e-4 * max(1.0, ref.abs().max().item()), err
+    # parameter gradients (split-K over the pixels, gamma folded in as a device scalar)
+    from ccnet_b200.functional import qkv_project_wgrad, qkv_wgrad_eligible
+    assert qkv_wgrad_eligible(C, C // 8)
+    scale = torch.tensor([0.75], device=dev)
+    outs = qkv_project_wgrad(xd, *(g.to(dev).contiguous(memory_format=torch.channels_last) for g in (gq, gk, gv)), scale=scale)
+    for i, g in enumerate((gq, gk, gv)):
+        gm = g.double().permute(0, 2, 3, 1).reshape(-1, g.shape[1])
+        rw, rb = 0.75 * (gm.t() @ xm), 0.75 * gm.sum(0)
+        ew = (outs[2 * i].cpu().double() - rw).abs().max().item()
+        eb = (outs[2 * i + 1].cpu().double() - rb).abs().max().item()
+        assert ew <= 1e-4 * max(1.0, rw.abs().max().item()), (i, ew)
+        assert eb <= 1e-4 * max(1.0, rb.abs().max().item(), rw.abs().max().item()), (i, eb)
 
 
 def test_fused_module_step_c512_vs_oracle_module():
@@ -454,3 +466,27 @@ def test_fused_module_step_c512_vs_oracle_module():
         r = rp[n].grad
         scale = rp[n.replace(".bias", ".weight")].grad.abs().max().item() if n.endswith(".bias") else r.abs().max().item()
         assert (p.grad.cpu() - r).abs().max().item() <= 2e-3 * max(1.0, scale), n
+
+
+def test_torch_ops_match_the_functional_path_and_differentiate():
+    """torch.ops.cca.forward / backward / forward_residual give the same bits as ccnet_b200.functional and carry
+    autograd; opcheck validates the registration (schema, fake tensor, autograd) on real tensors."""
+    from ccnet_b200 import cca_backward, cca_forward
+    dev = _dev()
+    q, k, v = (t.to(dev) for t in _rand_qkv(2, 16, 64, 9, 11, seed=4))
+    out, lse = torch.ops.cca.forward(q, k, v)
+    ro, rl = cca_forward(q, k, v)
+    assert torch.equal(out, ro) and torch.equal(lse, rl)
+    qg, kg, vg = (t.clone().requires_grad_(True) for t in (q, k, v))
+    o2, _ = torch.ops.cca.forward(qg, kg, vg)
+    do = torch.randn_like(o2)
+    o2.backward(do)
+    rq, rk, rv = cca_backward(do, q, k, v, ro, rl)
+    assert torch.equal(qg.grad, rq) and torch.equal(kg.grad, rk) and torch.equal(vg.grad, rv)
+    x = torch.randn_like(v).requires_grad_(True)
+    gamma = torch.tensor([0.3], device=dev, requires_grad=True)
+    y, _, _ = torch.ops.cca.forward_residual(q, k, v, x, gamma)
+    assert torch.allclose(y, 0.3 * ro + x.detach(), atol=1e-6)
+    y.backward(do)
+    assert torch.allclose(x.grad, do) and torch.allclose(gamma.grad, (do * ro).sum().reshape(1), rtol=1e-4)
+    torch.library.opcheck(torch.ops.cca.forward.default, (q, k, v), test_utils=("test_schema", "test_faketensor"))

@@ -85,3 +85,20 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(root, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
     assert "oracle" not in open(os.path.join(ROOT, "cc_attention", "__init__.py")).read().replace("oracle/", "")
+
+
+def test_torch_ops_are_registered_with_fake_implementations():
+    """torch.ops.cca.{forward, backward, forward_residual} exist and shape-infer under FakeTensorMode, so a
+    traced / compiled networks/ccnet.py does not graph-break on the operator."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    assert all(hasattr(torch.ops.cca, n) for n in ("forward", "backward", "forward_residual"))
+    with FakeTensorMode():
+        q = torch.empty(2, 8, 5, 6, device="cuda")
+        v = torch.empty(2, 64, 5, 6, device="cuda")
+        out, lse = torch.ops.cca.forward(q, q, v)
+        assert out.shape == v.shape and out.dtype == v.dtype and lse.shape == (2, 5, 6) and lse.dtype == torch.float32
+        dq, dk, dv = torch.ops.cca.backward(out, q, q, v, out, lse)
+        assert dq.shape == q.shape and dv.shape == v.shape
+        y, lse2, o2 = torch.ops.cca.forward_residual(q, q, v, v, torch.empty(1, device="cuda"))
+        assert y.shape == v.shape and lse2.shape == lse.shape and o2.shape == v.shape
+    torch.library.opcheck  # noqa: B018  (present in this torch; the GPU suite runs it on real tensors)
