@@ -408,6 +408,8 @@ def run_ours(args):
             fn()
         for _ in range(iters):
             flush.zero_()
+            torch.cuda._sleep(300000)          # ~0.15 ms of GPU spin: the host enqueues the op's launches meanwhile, so the
+                                               # events bracket back-to-back kernels, not host launch latency
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()

@@ -80,6 +80,7 @@ int cca_b200_version(void) { return CCA_B200_VERSION; }
 // A/B and profiling aids of debug builds (`python -m ccnet_b200.build --debug`); not part of the ABI, absent from release builds
 CCA_API void cca_b200__set_debug_buffer(void *p) { set_tc_debug_buffer(p); }
 CCA_API void cca_b200__set_bwd_debug_buffer(void *p) { set_tc_bwd_debug_buffer(p); }
+CCA_API void cca_b200__set_stats_debug_buffer(void *p) { set_tc_stats_debug_buffer(p); }
 CCA_API void cca_b200__set_pdl(int on) { set_tc_pdl(on); }
 CCA_API void cca_b200__set_zero_ahead(int n) { set_tc_zero_ahead(n); }
 CCA_API void cca_b200__set_delta_mode(int m) { set_tc_delta_mode(m); }

@@ -45,7 +45,7 @@ struct BwdParams {
     int C, Cq;
     long npix;
     const float *lse;
-    float *delta;              // [B,H,W] (delta_mode 1 only)
+    float *delta;              // [B,H,W] <dout, out> per pixel, written by the producer items (first bytes of the workspace)
     unsigned int *zdone;       // [B] zero shares of sample b completed
     unsigned int *ddone;       // [B] delta producers of sample b done (delta_mode 1)
     int delta_mode;            // 0: every item computes its own delta; 1: column / first-key-block items produce, the rest wait
@@ -74,50 +74,63 @@ template <int LK, bool BF> struct BwdSmem {
     static constexpr int kNLd = BF ? 6 : 5;                // every slot is the UMMA operand itself: a bf16 tile as loaded, an fp32
                                                            // tile once the converters have rewritten it in place (hi/lo planes)
     static constexpr int off_ld = 0;                       // kNLd load slots
-    static constexpr int off_out = off_ld + kNLd * T::kSlot; // 1 out slot (the epilogue has slack; the store warp drives it)
-    static constexpr int off_p = off_out + T::kSlot;       // P / dS planes (hi, lo); M=128 over-reads of a slot land in the next slot / here
+    static constexpr int kNOut = BF ? 3 : 1;               // staging slots (fp32: shared memory is full; bf16: the epilogue -> TMA
+                                                           // store -> slot-free chain of a single slot paced the whole item)
+    static constexpr int off_out = off_ld + kNLd * T::kSlot;
+    static constexpr int off_p = off_out + kNOut * T::kSlot; // P / dS planes (hi, lo); M=128 over-reads of a slot land in the next slot / here
     static constexpr int off_tail = off_p + T::kP + (16 - LK / 8) * T::kPlane;   // pad for the P^T over-read (16 planes of 8 key pixels)
     static constexpr int off_zero = off_tail + (128 - LK) * 16 + 256;            // zero tile of the zero-ahead copies
-    static constexpr int off_dpart = off_zero + kZeroBuf;  // float [2][128]: per-pixel delta halves from the converters
-    static constexpr int off_bar = off_dpart + 1024;
-    static constexpr int kBytes = off_bar + 8 * 40 + 32;
+    static constexpr int off_dpart = off_zero + kZeroBuf;  // float [2][128]: per-pixel delta halves from the converters, then
+                                                           // unsigned [8]: readers of an O slot (one counter per ring slot)
+    static constexpr int off_bar = off_dpart + 1024 + 32;
+    static constexpr int kBytes = off_bar + 8 * 48 + 32;
     static_assert(kBytes <= 232448, "shared memory budget");
 };
 
 enum { B_LD_FULL = 0, B_LD_EMPTY = 6, B_OP_FULL = 12, B_S_FULL = 18, B_S_EMPTY = 20, B_P_FULL = 22,
        B_P_EMPTY = 23, B_O_FULL = 24, B_O_EMPTY = 26, B_OUT_FULL = 28, B_STAGED = 29, B_DP_FULL = 30, B_DS_FULL = 31,
-       B_DELTA_FULL = 32, B_DELTA_EMPTY = 33, B_COUNT = 34 };
+       B_DELTA_FULL = 32, B_DELTA_EMPTY = 33, B_OUT_FREE = 34, B_STAGED_W = 37, B_COUNT = 43 };   // B_OUT_FREE[slot], B_STAGED_W[store warp][slot]
 
 // does this item compute delta itself (its ring carries the O chunks)?
 __device__ __forceinline__ bool calc_delta(const BwdParams &p, const Item &it) { return p.delta_mode == 0 || (it.col && it.ik == 0); }
 
 // Converter step for a (dO, O) pair of ring slots: returns this thread's part of sum_c dO[r][c] * O[r][c] over its 32 channels of
-// the chunk and (fp32) rewrites the dO slot in place as bf16 hi/lo planes.  All 256 converter threads; thread 0 releases the O slot.
+// the chunk and (fp32) rewrites the dO slot in place as bf16 hi/lo planes (layout of convert_slot_inplace: two independent
+// groups of 128 threads, one per 32-channel box).  The O slot goes back to the producer once BOTH groups have read it: the
+// second group leader to bump o_cnt arrives on the slot's LD_EMPTY barrier.
 template <int LK, bool BF>
-__device__ __forceinline__ float convert_dot(uint8_t *dslot, const uint8_t *oslot, int t, uint64_t *o_empty)
+__device__ __forceinline__ float convert_dot(uint8_t *dslot, const uint8_t *oslot, int t, uint64_t *o_empty, unsigned int *o_cnt)
 {
     using T = Tiles<LK, BF>;
-    const int r = t & 127, half = t >> 7;
+    const int r = t & 127, grp = t >> 7;
     const int rr = r < LK ? r : LK - 1;
     const int sw = rr & 7;
     float acc = 0.f;
+    auto group_sync_and_release = [&]() {
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 3, 128;" ::: "memory");
+        if (r == 0 && atomicAdd(o_cnt, 1u) == 1u) {       // both groups have read the O tile
+            *o_cnt = 0u;
+            mbar_arrive(o_empty);
+        }
+    };
     if constexpr (BF) {
         const uint8_t *a = dslot + rr * 128, *b = oslot + rr * 128;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int j = half * 4 + i;
+            const int j = grp * 4 + i;
             const uint4 x = *reinterpret_cast<const uint4 *>(a + ((j ^ sw) * 16));
             const uint4 y = *reinterpret_cast<const uint4 *>(b + ((j ^ sw) * 16));
             const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc += bf_lo(xw[e]) * bf_lo(yw[e]) + bf_hi(xw[e]) * bf_hi(yw[e]);
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(kConvThreads) : "memory");
-        if (t == 0) mbar_arrive(o_empty);
+        group_sync_and_release();
     } else {
         float4 raw[8];
-        const uint8_t *src = dslot + rr * 128 + half * T::kTile;
-        const uint8_t *osrc = oslot + rr * 128 + half * T::kTile;
+        uint8_t *box = dslot + grp * T::kTile;
+        const uint8_t *src = box + rr * 128;
+        const uint8_t *osrc = oslot + grp * T::kTile + rr * 128;
 #pragma unroll
         for (int j = 0; j < 8; ++j) raw[j] = *reinterpret_cast<const float4 *>(src + ((j ^ sw) * 16));
 #pragma unroll
@@ -125,18 +138,17 @@ __device__ __forceinline__ float convert_dot(uint8_t *dslot, const uint8_t *oslo
             const float4 o = *reinterpret_cast<const float4 *>(osrc + ((j ^ sw) * 16));
             acc += raw[j].x * o.x + raw[j].y * o.y + raw[j].z * o.z + raw[j].w * o.w;
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(kConvThreads) : "memory");
-        if (t == 0) mbar_arrive(o_empty);
+        group_sync_and_release();
         if (r < LK) {
-            uint8_t *dh = dslot + r * 16 + half * 4 * T::kPlane, *dl = dh + 8 * T::kPlane;
+            uint8_t *d = box + r * 16;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float4 a = raw[2 * j], b = raw[2 * j + 1];
                 const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
                 uint4 hi, lo;
                 split8(v, hi, lo);
-                *reinterpret_cast<uint4 *>(dh + j * T::kPlane) = hi;
-                *reinterpret_cast<uint4 *>(dl + j * T::kPlane) = lo;
+                *reinterpret_cast<uint4 *>(d + j * T::kPStride) = hi;
+                *reinterpret_cast<uint4 *>(d + j * T::kPStride + T::kLoOff) = lo;
             }
         }
     }
@@ -162,10 +174,12 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
     using S = BwdSmem<LK, BF>;
     constexpr int TERMS = BF ? 1 : 3;
     constexpr int kNLd = S::kNLd;
+    constexpr int kNOut = S::kNOut;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S::off_bar);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::off_bar + 8 * B_COUNT);
     float *dpart = reinterpret_cast<float *>(smem + S::off_dpart);
+    unsigned int *o_cnt = reinterpret_cast<unsigned int *>(smem + S::off_dpart + 1024);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NCH = p.C / kNC;
     const int KQ = p.Cq / 16;
@@ -178,7 +192,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             mbar_init(&bars[B_LD_FULL + i], 1); mbar_init(&bars[B_LD_EMPTY + i], 1); mbar_init(&bars[B_OP_FULL + i], kConvThreads);
         }
         for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_O_FULL + i], 1); mbar_init(&bars[B_O_EMPTY + i], 128); }
-        mbar_init(&bars[B_OUT_FULL], 1); mbar_init(&bars[B_STAGED], 128);
+        for (int i = 0; i < 3; ++i) { mbar_init(&bars[B_OUT_FREE + i], 1); mbar_init(&bars[B_STAGED_W + i], 128); mbar_init(&bars[B_STAGED_W + 3 + i], 128); }
         for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_S_FULL + i], 1); mbar_init(&bars[B_S_EMPTY + i], 128); }
         mbar_init(&bars[B_P_FULL], 128); mbar_init(&bars[B_P_EMPTY], 1);
         mbar_init(&bars[B_DP_FULL], 1);  mbar_init(&bars[B_DS_FULL], 128);
@@ -192,6 +206,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
         reinterpret_cast<uint4 *>(smem + S::off_zero)[tid] = make_uint4(0, 0, 0, 0);
         fence_proxy_async();
     }
+    if (tid < 8) o_cnt[tid] = 0u;
     if (warp == 0) tmem_alloc<kTmemCols>(tmem_slot);
     tc_fence_before();
     __syncthreads();
@@ -255,7 +270,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             const uint32_t id_mn_mn = instr_desc(kFmtBF16, kFmtBF16, 128, kNC, true, true);    // dV, dK: A^T planes x channel planes
             const uint32_t id_k_mn = instr_desc(kFmtBF16, kFmtBF16, 128, kNC, false, true);    // dQ
             const uint32_t pb = smem_u32(smem + S::off_p);
-            const uint32_t LO8 = 8 * T::kPlane, LOP = T::kPP * T::kPlane;
+            const uint32_t LO8 = BF ? 0 : T::kLoOff, LOP = T::kPP * T::kPlane;     // channel tiles: hi -> lo plane; P / dS planes: hi block -> lo block
             uint32_t u = 0, oc = 0;
             int dbg_n = lane == 0 ? 0 : 512;
             (void)dbg_n;
@@ -268,8 +283,8 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             auto free_op = [&](uint32_t g) { commit_to(&bars[B_LD_EMPTY + g % kNLd]); };
             // channel-tile operand parameters: (k-step, lbo, sbo, layout) when the contraction runs over channels (kmaj) or
             // over pixels (mnmaj)
-            constexpr uint32_t KS_K = BF ? 32 : 2 * T::kPlane, LBO_K = BF ? 16 : T::kPlane, SBO_K = BF ? 1024 : 128;
-            constexpr uint32_t KS_MN = BF ? 2048 : 256, LBO_MN = BF ? 16 : 128, SBO_MN = BF ? 1024 : T::kPlane;
+            constexpr uint32_t KS_K = BF ? 32 : 2 * T::kPStride, LBO_K = BF ? 16 : T::kPStride, SBO_K = BF ? 1024 : 128;
+            constexpr uint32_t KS_MN = BF ? 2048 : 256, LBO_MN = BF ? 16 : 128, SBO_MN = BF ? 1024 : T::kPStride;
             constexpr uint32_t LAY = BF ? kSw128 : 0;
             auto issue_s = [&](int k) {                       // S(k) = Q K^T into S buffer k&1
                 const uint32_t q = opb(u), kk = opb(u + 1);
@@ -336,15 +351,19 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                 }
                 CCA_STAMP(2);
             }
-        } else if (warp == kWarpStore) {
-            // =============================== store warp (one lane): the output staging slot <-> global ===============================
+        } else if (warp >= kWarpStore) {
+            // =============================== store warps (one lane each): the output staging slot -> global ===============================
+            // Two warps alternate items: while one waits for the global completion of its item's stores (to publish them), the
+            // other already issues the next item's tiles.
             if (lane == 0) {
-                uint8_t *slot = smem + S::off_out;
                 pdl_wait();                                // prep kernel complete: counters (and the first samples of dq/dk/dv) cleared
                 const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
                 int pending = -1;
-                uint32_t c = 0;
-                for (int k = 0; k < nk; ++k) {
+                // each store warp has its own STAGED barriers (a parity wait must never fall a whole phase pair behind)
+                const int sel = warp - kWarpStore;
+                uint32_t use[3] = {0, 0, 0};
+                for (int k = sel; k < nk; k += 2) {
+                    uint32_t c = (uint32_t)k * NO;         // global tile index (selects the staging slot)
                     const Item it = item_of(k);
                     const bool prod = p.out_mode == 1 && is_producer(it);
                     const int zb = it.b + p.ahead;
@@ -366,10 +385,10 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                         const int c0 = i < NCH ? i * kNC : 0;
                         const int start = i == NCH ? it.q0 : it.k0;
                         const int cw = it.col ? it.line : start, ch = it.col ? start : it.line;
-                        // slot is free once the previous store has been read out of shared memory
-                        tma_store_wait_read<0>();
-                        mbar_arrive(&bars[B_OUT_FULL]);
-                        mbar_wait(&bars[B_STAGED], c & 1);
+                        const int os = c % kNOut;
+                        uint8_t *slot = smem + S::off_out + os * T::kSlot;
+                        mbar_wait(&bars[B_STAGED_W + sel * 3 + os], use[os] & 1);
+                        ++use[os];
                         if (i == 0) {
                             if (pending >= 0) {
                                 tma_store_wait_all<0>();
@@ -401,6 +420,8 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                             if constexpr (!BF) tma_reduce_add_4d(m, slot + T::kTile, c0 + 32, cw, ch, it.b);
                         }
                         tma_store_commit();
+                        tma_store_wait_read<0>();          // the tile has been read out of shared memory: hand the slot back
+                        mbar_arrive(&bars[B_OUT_FREE + os]);
                     }
                     if (prod) {                            // publish: all stores of this item have completed
                         tma_store_wait_all<0>();
@@ -419,17 +440,35 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
         (void)dbg_n;
         uint32_t g = 0, ncalc = 0;
         // every ring slot passes through the converters (bf16 tiles only for the hand-shake: OP_FULL is what the MMA warp
-        // waits for in both dtypes, so a slot the converters read for delta is never released before they are done)
+        // waits for in both dtypes, so a slot the converters read for delta is never released before they are done).
+        // A converted slot is fenced + published only after the NEXT slot's loads have been issued (see convert_slot_inplace).
+        uint32_t pend = 0;                                             // bit s: slot s converted, not yet published
+        auto publish = [&]() {
+            if (pend) {
+                if constexpr (!BF) fence_proxy_async();
+                for (int sl = 0; sl < kNLd; ++sl)
+                    if (pend & (1u << sl)) mbar_arrive(&bars[B_OP_FULL + sl]);
+                pend = 0;
+            }
+        };
+        auto wait_full = [&](uint32_t gg) {
+            const int slot = gg % kNLd;
+            if (!mbar_try_wait(&bars[B_LD_FULL + slot], (gg / kNLd) & 1)) {
+                publish();
+                mbar_wait(&bars[B_LD_FULL + slot], (gg / kNLd) & 1);
+            }
+        };
         auto conv = [&](int count) {
             for (int e = 0; e < count; ++e, ++g) {
                 const int slot = g % kNLd;
-                mbar_wait(&bars[B_LD_FULL + slot], (g / kNLd) & 1);
+                wait_full(g);
                 CCA_STAMP(1);
                 if constexpr (!BF) {
-                    convert_slot_inplace<LK>(smem + S::off_ld + slot * T::kSlot, t);
-                    fence_proxy_async();
+                    convert_slot_inplace<LK>(smem + S::off_ld + slot * T::kSlot, t, publish);
+                    pend |= 1u << slot;
+                } else {
+                    mbar_arrive(&bars[B_OP_FULL + slot]);              // bf16: nothing to convert, nothing to fence
                 }
-                mbar_arrive(&bars[B_OP_FULL + slot]);
                 CCA_STAMP(1);
             }
         };
@@ -441,18 +480,24 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                 conv(1);                                               // V
                 if (calc) {                                            // dO + O: dot products, then dO as operand
                     const int sd = g % kNLd, so = (g + 1) % kNLd;
-                    mbar_wait(&bars[B_LD_FULL + sd], (g / kNLd) & 1);
-                    mbar_wait(&bars[B_LD_FULL + so], ((g + 1) / kNLd) & 1);
-                    dacc += convert_dot<LK, BF>(smem + S::off_ld + sd * T::kSlot, smem + S::off_ld + so * T::kSlot, t, &bars[B_LD_EMPTY + so]);
-                    fence_proxy_async();
-                    mbar_arrive(&bars[B_OP_FULL + sd]);
-                    mbar_arrive(&bars[B_OP_FULL + so]);                // nobody waits for it; keeps the slot's phase in step
+                    wait_full(g);
+                    wait_full(g + 1);
+                    publish();
+                    dacc += convert_dot<LK, BF>(smem + S::off_ld + sd * T::kSlot, smem + S::off_ld + so * T::kSlot, t, &bars[B_LD_EMPTY + so],
+                                                o_cnt + so);
+                    if constexpr (!BF) {
+                        pend |= (1u << sd) | (1u << so);               // (nobody waits for the O slot; keeps its phase in step)
+                    } else {
+                        mbar_arrive(&bars[B_OP_FULL + sd]);
+                        mbar_arrive(&bars[B_OP_FULL + so]);
+                    }
                     g += 2;
                 } else {
                     conv(1);                                           // dO
                 }
             }
             if (calc) {                                                // hand the per-pixel sums to the P/dS group
+                publish();                                             // (never block on anything but a load with a slot withheld)
                 mbar_wait(&bars[B_DELTA_EMPTY], (ncalc & 1) ^ 1);
                 dpart[(t >> 7) * 128 + (t & 127)] = dacc;
                 mbar_arrive(&bars[B_DELTA_FULL]);
@@ -461,6 +506,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             if (k + 1 < nk) conv(2);
             conv(2);
         }
+        publish();
     } else if (warp >= 4) {
         // =============================== P / dS group (128 threads, TMEM lane == query pixel) ===============================
         reg_inc<kRegsSoft>();
@@ -537,8 +583,10 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                 dl = dpart[r] + dpart[128 + r];
                 mbar_arrive(&bars[B_DELTA_EMPTY]);
                 ++ncalc;
-                if (p.delta_mode == 1) {                       // publish for the other items of the sample
-                    if (rvalid) p.delta[pix] = dl;
+                // delta[B,H,W] always ends up in the workspace (the caller's d gamma = sum of it); in mode 1 it is also how the
+                // other items of the sample get it
+                if (rvalid && is_producer(it)) p.delta[pix] = dl;
+                if (p.delta_mode == 1) {
                     named_bar_sync(2, 128);
                     if (r == 0) { __threadfence(); atomicAdd(p.ddone + it.b, 1u); }
                 }
@@ -596,15 +644,16 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
         reg_inc<kRegsEpi>();
         const int r = tid;
         const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
-        uint8_t *slot = smem + S::off_out;
         uint32_t oc = 0;
         int dbg_n = tid == 0 ? 0 : 512;
         (void)dbg_n;
         for (int k = 0; k < nk; ++k) {
             for (int i = 0; i < NO; ++i, ++oc) {
                 const int ob = oc & 1;
+                const int os = oc % kNOut;
+                uint8_t *slot = smem + S::off_out + os * T::kSlot;
                 CCA_STAMP(4);
-                mbar_wait(&bars[B_OUT_FULL], oc & 1);                 // staging slot free
+                mbar_wait(&bars[B_OUT_FREE + os], ((oc / kNOut) & 1) ^ 1);   // the store of tile oc - kNOut has left the slot
                 mbar_wait(&bars[B_O_FULL + ob], (oc >> 1) & 1);
                 tc_fence_after();
                 CCA_STAMP(4);
@@ -633,7 +682,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                     }
                 }
                 fence_proxy_async();
-                mbar_arrive(&bars[B_STAGED]);
+                mbar_arrive(&bars[B_STAGED_W + (k & 1) * 3 + os]);
                 CCA_STAMP(4);
             }
         }
@@ -683,8 +732,10 @@ cudaError_t launch_bwd(const void *dout, const void *q, const void *k, const voi
     p.delta_mode = delta_mode;
     const bool one_tile = p.sp.col.nt == 1 && p.sp.row.nt == 1;
     p.out_mode = one_tile ? 1 : 0;
-    p.lag = tc_lag() == 1 ? 1 : 0;                 // default (-1): sample after sample (the backward's per-sample working set is
-                                                   // too large for two samples to share L2)
+    // item order: lagged by default (measured 0.30 ms vs 0.35 ms at BASELINE config 2: the consumers' waits for their producers
+    // cost more than the larger L2 working set).  Zero-ahead (tiled lines) needs the plain order: an item of sample b waits for
+    // the zero shares issued by ALL items of sample b-1, and in the lagged order some of those come later in the walk.
+    p.lag = (p.out_mode == 1 && tc_lag() != 0) ? 1 : 0;
     p.hints = tc_l2_hints();
     p.dq = reinterpret_cast<uint8_t *>(dq); p.dk = reinterpret_cast<uint8_t *>(dk); p.dv = reinterpret_cast<uint8_t *>(dv);
     const long es = BF ? 2 : 4;
@@ -743,8 +794,8 @@ cudaError_t tc_backward(const void *dout, const void *q, const void *k, const vo
     const bool bf = dtype == CCA_BF16;
     int ahead = tc_zero_ahead();
     if (ahead < 1) ahead = 1;
-    int mode = tc_delta_mode();                       // -1: automatic
-    if (mode < 0) mode = (sp.col.nt == 1 && sp.row.nt == 1) ? 1 : 0;
+    int mode = tc_delta_mode();                       // -1: automatic = producers compute delta for their sample (the consumers
+    if (mode < 0) mode = 1;                           // only ever wait for lower-indexed items, tiled or not)
     if (bf)
         return lk == 80 ? launch_bwd<80, true>(dout, q, k, v, out, lse, delta, counters, dq, dk, dv, d, ahead, mode, st, why)
                         : launch_bwd<112, true>(dout, q, k, v, out, lse, delta, counters, dq, dk, dv, d, ahead, mode, st, why);

@@ -42,6 +42,10 @@ template <int LK, bool BF = false> struct Tiles {
     static constexpr int kTile = LK * 128;             // [LK px][128 B] = 32 fp32 or 64 bf16 channels, SWIZZLE_128B
     static constexpr int kSlot = BF ? kTile : 2 * kTile; // 64 channels
     static constexpr int kPlane = LK * 16;             // operand plane: LK rows x 16 B (8 bf16)
+    // fp32 I/O: a converted slot holds its 8-channel planes as  hi0 lo0 hi1 lo1 ... hi7 lo7  (each 32-channel TMA box is rewritten
+    // inside its own bytes, so the two boxes of a slot are converted by two independent thread groups)
+    static constexpr int kPStride = 2 * kPlane;        // hi plane p -> hi plane p+1 (and lo -> lo)
+    static constexpr int kLoOff = kPlane;              // hi plane p -> lo plane p
     static constexpr int kTerms = BF ? 1 : 2;          // operand copies kept: hi (+ lo)
     static constexpr int kOp = kTerms * 8 * kPlane;    // 8 planes = 64 channels, per copy
     static constexpr int kPP = LK / 8;                 // planes of a [LK x LK] pixel-pixel matrix (P, dS)
@@ -84,34 +88,42 @@ __device__ __forceinline__ bool elect_one()
     return pred != 0;
 }
 
-// Converter: one staged slot ([LK px][64 ch] fp32 as two swizzled tiles) -> hi/lo operand planes
-// [8-channel chunk][pixel][16 B].  256 threads: thread t handles pixel (t & 127), octets 4*(t>>7)..+3.
-// fp32 tile -> bf16 hi/lo planes IN PLACE (the planes take exactly the bytes of the two fp32 tiles): every converter thread
-// reads and splits its 128 B first, all 256 meet on named barrier 1, then they overwrite the slot.
-template <int LK>
-__device__ __forceinline__ void convert_slot_inplace(uint8_t *slot, int t)
+// Converter: one staged slot ([LK px][64 ch] fp32 as two swizzled 32-channel TMA boxes) -> bf16 hi/lo operand planes
+// [8-channel chunk][pixel][16 B], IN PLACE.  Each box is rewritten inside its own bytes (planes hi0 lo0 .. hi3 lo3 of its 32
+// channels take exactly the box's LK x 128 B), so the two boxes are handled by two independent groups of 128 threads (group =
+// t >> 7, one thread per pixel row): every thread reads and splits its 128 B, the group meets on its own named barrier (1 or
+// 3), then overwrites.  The groups drift apart, which overlaps one group's shared-memory phase with the other's ALU phase.
+// `mid` runs after the loads have been issued and before the group barrier: the callers use it to fence + publish the PREVIOUS
+// slot there, so that the proxy fence (which waits for the thread's outstanding shared-memory stores to drain, a few hundred
+// cycles right after 8 STS.128) overlaps the load latency of this slot instead of sitting on the critical path.
+struct ConvertNoMid { __device__ __forceinline__ void operator()() const {} };
+template <int LK, typename Mid = ConvertNoMid>
+__device__ __forceinline__ void convert_slot_inplace(uint8_t *slot, int t, Mid mid = Mid())
 {
     using T = Tiles<LK, false>;
-    const int r = t & 127, half = t >> 7;
+    const int r = t & 127, grp = t >> 7;
+    uint8_t *box = slot + grp * T::kTile;
     float4 raw[8];                                              // the thread's 32 channels; split only after the barrier (fewer live registers)
     {
         const int rr = r < LK ? r : LK - 1;                     // idle threads re-read the last row (unconditional loads keep raw[] in registers)
-        const uint8_t *src = slot + rr * 128 + half * T::kTile; // octets 0-3 live in tile 0, 4-7 in tile 1
+        const uint8_t *src = box + rr * 128;
         const int sw = rr & 7;
 #pragma unroll
         for (int j = 0; j < 8; ++j) raw[j] = *reinterpret_cast<const float4 *>(src + ((j ^ sw) * 16));
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(kConvThreads) : "memory");
+    mid();
+    if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+    else asm volatile("bar.sync 3, 128;" ::: "memory");
     if (r < LK) {
-        uint8_t *dh = slot + r * 16 + half * 4 * T::kPlane, *dl = dh + 8 * T::kPlane;
+        uint8_t *d = box + r * 16;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float4 a = raw[2 * j], b = raw[2 * j + 1];
             const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
             uint4 hi, lo;
             split8(v, hi, lo);
-            *reinterpret_cast<uint4 *>(dh + j * T::kPlane) = hi;
-            *reinterpret_cast<uint4 *>(dl + j * T::kPlane) = lo;
+            *reinterpret_cast<uint4 *>(d + j * T::kPStride) = hi;
+            *reinterpret_cast<uint4 *>(d + j * T::kPStride + T::kLoOff) = lo;
         }
     }
 }

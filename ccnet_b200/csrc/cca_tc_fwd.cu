@@ -46,7 +46,8 @@ constexpr int kTmemCols = 512;      // S [0,128)   P double buffer (hi/lo) [128,
 constexpr int kTmemP = 128, kTmemO = 384, kNOB = 2;
 constexpr int kRegsSoft = 104, kRegsEpi = 128, kRegsConvF = 88;
 static_assert(reg_pool_ok(kRegsSoft, kRegsEpi, kRegsConvF), "setmaxnreg pool");
-constexpr int kNOut = 2;            // staging slots
+constexpr int kNOutMax = 4;         // staging slots: 2 (fp32: shared memory is full) or 4 (bf16: 14 KB each; the store path -- one TMA
+                                    // instruction per chunk, ~500 cycles until the tile has left shared memory -- needs the slack)
 
 struct FwdParams {
     ItemSpace sp;
@@ -72,18 +73,19 @@ struct FwdParams {
 template <int LK, bool BF> struct FwdSmem {
     using T = Tiles<LK, BF>;
     static constexpr int kNLd = BF ? 8 : 6;
+    static constexpr int kNOut = BF ? 4 : 2;
     static constexpr int off_ld = 0;                          // kNLd load slots; every slot is the UMMA operand itself: a bf16 tile as
                                                               // loaded, an fp32 tile once the converters have rewritten it in place
     static constexpr int off_out = off_ld + kNLd * T::kSlot;  // kNOut staging slots
     // (An M=128 MMA reads (128 - LK) rows past the end of its Q slot: they land in the next slot / the staging slots and
     // only feed S rows >= LK, which are discarded.)
     static constexpr int off_bar = off_out + kNOut * T::kSlot + 1024;
-    static constexpr int kBytes = off_bar + 8 * 40 + 32;
+    static constexpr int kBytes = off_bar + 8 * 48 + 32;
     static_assert(kBytes <= 232448, "shared memory budget");
 };
 
 enum { B_LD_FULL = 0, B_LD_EMPTY = 8, B_OP_FULL = 16, B_S_FULL = 24, B_S_EMPTY = 25, B_P_FULL = 26,
-       B_P_EMPTY = 28, B_O_FULL = 30, B_O_EMPTY = 32, B_OUT_FREE = 34, B_STAGED = 36, B_COUNT = 38 };
+       B_P_EMPTY = 28, B_O_FULL = 30, B_O_EMPTY = 32, B_OUT_FREE = 34, B_STAGED = 38, B_COUNT = 46 };   // B_OUT_FREE: [slot], B_STAGED: [store warp][slot]
 
 template <int LK, bool BF>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -95,6 +97,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
     using T = Tiles<LK, BF>;
     using S = FwdSmem<LK, BF>;
     constexpr int kNLd = S::kNLd;
+    constexpr int kNOut = S::kNOut;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S::off_bar);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::off_bar + 8 * B_COUNT);
@@ -112,7 +115,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             mbar_init(&bars[B_LD_FULL + i], 1); mbar_init(&bars[B_LD_EMPTY + i], 1); mbar_init(&bars[B_OP_FULL + i], kConvThreads);
         }
         for (int i = 0; i < kNOB; ++i) { mbar_init(&bars[B_O_FULL + i], 1); mbar_init(&bars[B_O_EMPTY + i], 128); }
-        for (int i = 0; i < kNOut; ++i) { mbar_init(&bars[B_OUT_FREE + i], 1); mbar_init(&bars[B_STAGED + i], 128); }
+        for (int i = 0; i < kNOut; ++i) { mbar_init(&bars[B_OUT_FREE + i], 1); mbar_init(&bars[B_STAGED + i], 128); mbar_init(&bars[B_STAGED + kNOut + i], 128); }
         mbar_init(&bars[B_S_FULL], 1); mbar_init(&bars[B_S_EMPTY], 128);
         for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_P_FULL + i], 128); mbar_init(&bars[B_P_EMPTY + i], 1); }
         fence_mbar_init();
@@ -191,9 +194,9 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                         mma_split3<1>(tmem, smem_desc(qb + ks * 32, 16, 1024, kSw128), 0, smem_desc(kb + ks * 32, 16, 1024, kSw128), 0,
                                       idesc_s, ks > 0);
                     } else {
-                        const uint32_t ao = ks * 2 * T::kPlane;
-                        mma_split3<3>(tmem, smem_desc(qb + ao, T::kPlane, 128), smem_desc(qb + 8 * T::kPlane + ao, T::kPlane, 128),
-                                      smem_desc(kb + ao, T::kPlane, 128), smem_desc(kb + 8 * T::kPlane + ao, T::kPlane, 128),
+                        const uint32_t ao = ks * 2 * T::kPStride;
+                        mma_split3<3>(tmem, smem_desc(qb + ao, T::kPStride, 128), smem_desc(qb + T::kLoOff + ao, T::kPStride, 128),
+                                      smem_desc(kb + ao, T::kPStride, 128), smem_desc(kb + T::kLoOff + ao, T::kPStride, 128),
                                       idesc_s, ks > 0);
                     }
                 }
@@ -224,8 +227,8 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                             if constexpr (BF) {
                                 mma_f16_ts(d, ph, smem_desc(vb + ks * 2048, 16, 1024, kSw128), idesc_o, ks > 0);
                             } else {
-                                const uint64_t vh = smem_desc(vb + ks * 256, 128, T::kPlane);
-                                const uint64_t vl = smem_desc(vb + 8 * T::kPlane + ks * 256, 128, T::kPlane);
+                                const uint64_t vh = smem_desc(vb + ks * 256, 128, T::kPStride);
+                                const uint64_t vl = smem_desc(vb + T::kLoOff + ks * 256, 128, T::kPStride);
                                 mma_f16_ts(d, ph, vh, idesc_o, ks > 0);
                                 mma_f16_ts(d, ph, vl, idesc_o, true);
                                 mma_f16_ts(d, pl, vh, idesc_o, true);
@@ -239,13 +242,19 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                 }
                 commit_to(&bars[B_P_EMPTY + (k & 1)]);
             }
-        } else if (warp == kWarpStore) {
-            // =============================== store warp (one lane) ===============================
+        } else if (warp >= kWarpStore) {
+            // =============================== store warps (one lane each) ===============================
+            // Two warps alternate items: while one waits for the global completion of its producer item's stores (to publish
+            // them), the other already issues the next item's tiles.
             if (lane == 0) {
                 pdl_wait();                                // statistics kernel complete: the counters are cleared
                 const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
                 const bool one_tile = p.sp.col.nt == 1 && p.sp.row.nt == 1;
-                for (int k = 0; k < nk; ++k) {
+                // each store warp has its own STAGED barriers (a parity wait must never fall a whole phase pair behind, which
+                // it would if it shared the barrier with the chunks of the other warp's items)
+                const int sel = warp - kWarpStore;
+                uint32_t use[kNOutMax] = {0, 0, 0, 0};
+                for (int k = sel; k < nk; k += 2) {
                     const Item it = item_of(k);
                     const bool prod = is_producer(it);
                     const CUtensorMap *mo = it.col ? &moc : &mor;          // box = one tile of this direction, exactly
@@ -253,7 +262,8 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                     for (int n = 0; n < NCH; ++n) {
                         const uint32_t c = (uint32_t)k * NCH + n;
                         const int os = c % kNOut;
-                        mbar_wait(&bars[B_STAGED + os], (c / kNOut) & 1);
+                        mbar_wait(&bars[B_STAGED + sel * kNOut + os], use[os] & 1);
+                        ++use[os];
                         if (n == 0 && !prod) {             // every producer of this sample has stored its tile
                             wait_count(p.cdone + it.b, (unsigned)p.sp.seg0);
                             fence_proxy_async_all();
@@ -278,7 +288,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                         tma_store_wait_read<0>();          // the tile has been read out of shared memory: hand the slot back
                         mbar_arrive(&bars[B_OUT_FREE + os]);
                     }
-                    if (prod) {                            // publish: the next chunk is a third of an item away, this wait is free
+                    if (prod) {                            // publish once the stores have completed (the other store warp carries on)
                         tma_store_wait_all<0>();
                         publish_count(p.cdone + it.b);
                     }
@@ -293,14 +303,25 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
         int dbg_n = t == 0 ? 0 : 512;
         (void)dbg_n;
         uint32_t g = 0;
+        int pend = -1;                                             // slot converted but not yet fenced / published
+        auto publish = [&]() {
+            if (pend >= 0) {
+                fence_proxy_async();
+                mbar_arrive(&bars[B_OP_FULL + pend]);
+                pend = -1;
+            }
+        };
         auto convert_next = [&](int count) {                       // the next `count` ring slots, whatever they hold
             for (int e = 0; e < count; ++e, ++g) {
                 const int slot = g % kNLd;
-                mbar_wait(&bars[B_LD_FULL + slot], (g / kNLd) & 1);
+                // the previous slot is published after this slot's loads are in flight -- unless this slot has not landed yet
+                if (!mbar_try_wait(&bars[B_LD_FULL + slot], (g / kNLd) & 1)) {
+                    publish();
+                    mbar_wait(&bars[B_LD_FULL + slot], (g / kNLd) & 1);
+                }
                 CCA_STAMP(1);
-                convert_slot_inplace<LK>(smem + S::off_ld + slot * T::kSlot, t);
-                fence_proxy_async();
-                mbar_arrive(&bars[B_OP_FULL + slot]);
+                convert_slot_inplace<LK>(smem + S::off_ld + slot * T::kSlot, t, publish);
+                pend = slot;
                 CCA_STAMP(1);
             }
         };
@@ -311,6 +332,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                     if (n == qkpos && k + 1 < nk) convert_next(2);
                     convert_next(1);
                 }
+            publish();
         }
     } else if (warp >= 4) {
         // =============================== softmax group (128 threads, TMEM lane == query pixel) ===============================
@@ -425,7 +447,7 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                     }
                 }
                 fence_proxy_async();
-                mbar_arrive(&bars[B_STAGED + os]);                       // the store warp takes over
+                mbar_arrive(&bars[B_STAGED + (k & 1) * kNOut + os]);     // the store warp of this item takes over
                 CCA_STAMP(4);
             }
         }

@@ -34,7 +34,17 @@ struct StatsParams {
     long zero_bytes;
     unsigned int *counters;       // n_counters words cleared
     int n_counters;
+    long long *dbg;               // timeline buffer (CTA 0), -DCCA_TIMELINE builds only
 };
+
+#ifdef CCA_TIMELINE
+#define CCA_STAMP(role)                                                                          \
+    do {                                                                                         \
+        if (p.dbg && blockIdx.x == 0 && dbg_n < 512) p.dbg[(role) * 512 + dbg_n++] = clock64();  \
+    } while (0)
+#else
+#define CCA_STAMP(role) do { } while (0)
+#endif
 
 template <int LK, bool BF> struct StatsSmem {
     using T = Tiles<LK, BF>;
@@ -82,6 +92,8 @@ cca_tc_stats_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_consta
     if (warp == kWarpProducer) {
         if (lane == 0) {
             uint32_t g = 0;
+            int dbg_n = 0;
+            (void)dbg_n;
             for (int k = 0; k < nk; ++k) {
                 const Item it = item_of(k);
                 for (int t = 0; t < 2; ++t, ++g) {
@@ -90,6 +102,7 @@ cca_tc_stats_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_consta
                     const int cw = it.col ? it.line : start, ch = it.col ? start : it.line;
                     const int slot = g % kNS;
                     mbar_wait(&bars[SB_LD_EMPTY + slot], ((g / kNS) & 1) ^ 1);
+                    CCA_STAMP(0);
                     uint8_t *dst = smem + S::off_ld + slot * T::kSlot;
                     mbar_expect_tx(&bars[SB_LD_FULL + slot], T::kSlot);
                     tma_load_4d(dst, m, &bars[SB_LD_FULL + slot], 0, cw, ch, it.b);
@@ -101,21 +114,25 @@ cca_tc_stats_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_consta
         const uint32_t idesc_s = instr_desc(kFmtBF16, kFmtBF16, 128, LK, false, false);
         const uint32_t ld_base = smem_u32(smem + S::off_ld);
         uint32_t g = 0;
+        int dbg_n = lane == 0 ? 0 : 512;
+        (void)dbg_n;
         for (int k = 0; k < nk; ++k, g += 2) {
             const uint32_t qb = ld_base + (g % kNS) * T::kSlot, kb = ld_base + ((g + 1) % kNS) * T::kSlot;
             mbar_wait(&bars[(BF ? SB_LD_FULL : SB_OP_FULL) + g % kNS], (g / kNS) & 1);
             mbar_wait(&bars[(BF ? SB_LD_FULL : SB_OP_FULL) + (g + 1) % kNS], ((g + 1) / kNS) & 1);
+            CCA_STAMP(2);
             mbar_wait(&bars[SB_S_EMPTY + (k % kNSB)], ((k / kNSB) & 1) ^ 1);
             tc_fence_after();
+            CCA_STAMP(2);
             const uint32_t d = tmem + (k % kNSB) * 128;
             for (int ks = 0; ks < KQ; ++ks) {
                 if constexpr (BF) {
                     mma_split3<1>(d, smem_desc(qb + ks * 32, 16, 1024, kSw128), 0, smem_desc(kb + ks * 32, 16, 1024, kSw128), 0,
                                   idesc_s, ks > 0);
                 } else {
-                    const uint32_t ao = ks * 2 * T::kPlane;
-                    mma_split3<3>(d, smem_desc(qb + ao, T::kPlane, 128), smem_desc(qb + 8 * T::kPlane + ao, T::kPlane, 128),
-                                  smem_desc(kb + ao, T::kPlane, 128), smem_desc(kb + 8 * T::kPlane + ao, T::kPlane, 128),
+                    const uint32_t ao = ks * 2 * T::kPStride;
+                    mma_split3<3>(d, smem_desc(qb + ao, T::kPStride, 128), smem_desc(qb + T::kLoOff + ao, T::kPStride, 128),
+                                  smem_desc(kb + ao, T::kPStride, 128), smem_desc(kb + T::kLoOff + ao, T::kPStride, 128),
                                   idesc_s, ks > 0);
                 }
             }
@@ -136,24 +153,43 @@ cca_tc_stats_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_consta
             for (int i = t; i < p.n_counters; i += 64) p.counters[i] = 0u;
     } else if (warp >= kWarpConv0) {
         const int t = tid - kWarpConv0 * 32;
+        int dbg_n = t == 0 ? 0 : 512;
+        (void)dbg_n;
         if constexpr (!BF) {
+            int pend = -1;                       // slot converted but not yet fenced / published (see convert_slot_inplace)
+            auto publish = [&]() {
+                if (pend >= 0) {
+                    fence_proxy_async();
+                    mbar_arrive(&bars[SB_OP_FULL + pend]);
+                    pend = -1;
+                }
+            };
             for (uint32_t g = 0; g < (uint32_t)(2 * nk); ++g) {
                 const int slot = g % kNS;
-                mbar_wait(&bars[SB_LD_FULL + slot], (g / kNS) & 1);
-                convert_slot_inplace<LK>(smem + S::off_ld + slot * T::kSlot, t);
-                fence_proxy_async();
-                mbar_arrive(&bars[SB_OP_FULL + slot]);
+                if (!mbar_try_wait(&bars[SB_LD_FULL + slot], (g / kNS) & 1)) {
+                    publish();
+                    mbar_wait(&bars[SB_LD_FULL + slot], (g / kNS) & 1);
+                }
+                CCA_STAMP(1);
+                convert_slot_inplace<LK>(smem + S::off_ld + slot * T::kSlot, t, publish);
+                pend = slot;
+                CCA_STAMP(1);
             }
+            publish();
         }
         (void)t;
     } else {
         // =============================== statistics groups (2 x 128 threads, TMEM lane == query pixel) ===============================
         const int grp = warp >> 2, r = tid & 127;
         const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        int dbg_n = tid == 0 ? 0 : 512;          // group 0 only (role 3)
+        (void)dbg_n;
         for (int k = grp; k < nk; k += 2) {
             const Item it = item_of(k);
+            CCA_STAMP(3);
             mbar_wait(&bars[SB_S_FULL + (k % kNSB)], (k / kNSB) & 1);
             tc_fence_after();
+            CCA_STAMP(3);
             const uint32_t ts = tl + (k % kNSB) * 128;
             const int self = it.col ? it.q0 + r - it.k0 : -1;      // masked key of this query (column branch only)
             // predicated path only for the 16-key chunks that hold the tail of the key block or the self entry of one of this
@@ -199,6 +235,7 @@ cca_tc_stats_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_consta
             }
             tc_fence_before();
             mbar_arrive(&bars[SB_S_EMPTY + (k % kNSB)]);
+            CCA_STAMP(3);
             if (r < it.lq) p.parts[(long)part_index(p.sp, it) * p.npix + item_pixel(p.sp, it, r)] = l > 0.f ? m + log2f(l) : -INFINITY;
         }
     }
@@ -206,6 +243,8 @@ cca_tc_stats_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_consta
     __syncthreads();
     if (warp == 0) tmem_dealloc<512>(tmem);
 }
+
+long long *g_stats_dbg = nullptr;
 
 template <int LK, bool BF>
 cudaError_t launch_stats(const void *q, const void *k, float *parts, void *zero_ptr, long zero_bytes, unsigned int *counters,
@@ -226,6 +265,7 @@ cudaError_t launch_stats(const void *q, const void *k, float *parts, void *zero_
     p.parts = parts;
     p.zero_ptr = reinterpret_cast<uint8_t *>(zero_ptr); p.zero_bytes = zero_bytes;
     p.counters = counters; p.n_counters = n_counters;
+    p.dbg = g_stats_dbg;
     auto kern = cca_tc_stats_kernel<LK, BF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, StatsSmem<LK, BF>::kBytes);
     if (e != cudaSuccess) return e;
@@ -237,6 +277,8 @@ cudaError_t launch_stats(const void *q, const void *k, float *parts, void *zero_
 }
 
 }  // namespace
+
+void set_tc_stats_debug_buffer(void *p) { g_stats_dbg = reinterpret_cast<long long *>(p); }
 
 // parts: [nparts][B*H*W] fp32.  Also clears zero_bytes bytes at zero_ptr and n_counters words at counters (both may be 0).
 cudaError_t tc_stats(const void *q, const void *k, float *parts, void *zero_ptr, long zero_bytes, unsigned int *counters,

@@ -77,8 +77,10 @@ def cca_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, impl: str = "
     return out, lse
 
 
-def cca_backward(dout, q, k, v, out, lse, impl: str = "auto"):
+def cca_backward(dout, q, k, v, out, lse, impl: str = "auto", want_delta: bool = False):
     """Gradients (dq, dk, dv) of ``cca_forward`` given dout and the saved forward tensors.
+    ``want_delta``: also return delta[B,H,W] = <dout, out> per pixel as a 4th value when the tensor-core kernels ran (they
+    leave it in the workspace; its sum is the gradient of the residual's gamma), else None.
 
     Same ``impl`` / memory-format rules as ``cca_forward``: the tensor-core kernels take and return
     channels-last tensors, the generic kernels NCHW-contiguous ones.
@@ -117,6 +119,9 @@ def cca_backward(dout, q, k, v, out, lse, impl: str = "auto"):
                                    ws.data_ptr(), ws.numel(), B, Cq, C, H, W, dt, flags,
                                    _stream_ptr(q.device))
     capi.check(rc, "cca_b200_backward")
+    if want_delta:
+        delta = ws[:B * H * W * 4].view(torch.float32).view(B, H, W) if use_tc else None
+        return dq, dk, dv, delta
     return dq, dk, dv
 
 

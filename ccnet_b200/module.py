@@ -74,11 +74,11 @@ class _FusedCCAStep(torch.autograd.Function):
         x, q, k, v, o, lse, wq, wk, wv, gamma = ctx.saved_tensors
         B, C, H, W = x.shape
         dy = dy.contiguous(memory_format=torch.channels_last)
-        dq, dk, dv = cca_backward(dy, q, k, v, o, lse, "tc")                # gradients w.r.t. q,k,v for dout = dy (gamma pending)
+        dq, dk, dv, delta = cca_backward(dy, q, k, v, o, lse, "tc", want_delta=True)   # for dout = dy (gamma pending)
         g = gamma.detach().to(dy.dtype).contiguous()
         dx = qkv_project_dgrad(dq, dk, dv, wq, wk, wv, scale=g)             # gamma rides on the packed weights
         dx += dy                                                            # the residual branch
-        dgamma = torch.dot(dy.reshape(-1), o.reshape(-1)).reshape(1)
+        dgamma = delta.sum().reshape(1)                                     # <dy, o>: the kernel's per-pixel delta, summed
         if qkv_wgrad_eligible(C, q.shape[1]):
             dwq, dbq, dwk, dbk, dwv, dbv = qkv_project_wgrad(x, dq, dk, dv, scale=g)
             shp = ctx.wshapes

@@ -94,9 +94,13 @@ def test_forward_tensor_core_vs_oracle_and_simt(shape):
         ro, rl = O.cca_forward(q.double(), k.double(), v.double())
         assert (out.cpu().double() - ro).abs().max().item() <= 5e-4
         assert (lse.cpu().double() - rl).abs().max().item() <= 5e-4
-    # channels-last inputs give bit-identical results (no hidden layout dependence)
+    # channels-last inputs give the same result (no hidden layout dependence): bit-identical with one tile per line (one
+    # store + one add per element); with tiled lines an element is the sum of 2*nt-1 adds whose order is not fixed
     out2, _ = cca_forward(qd.contiguous(memory_format=torch.channels_last), kd, vd.contiguous(memory_format=torch.channels_last), impl="tc")
-    assert torch.equal(out, out2)
+    if max(shape[3], shape[4]) <= 112:
+        assert torch.equal(out, out2)
+    else:
+        assert (out - out2).abs().max().item() <= 1e-5 * max(1.0, out.abs().max().item())
 
 
 @pytest.mark.parametrize("shape", [(2, 32, 256, 20, 97), (1, 64, 64, 112, 80), (3, 16, 64, 1, 5), (2, 16, 64, 5, 1),

@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out
+L=gpurun_out/stage10.log
+: > $L
+run() { echo "== $*" >> $L; timeout 600 "$@" >> $L 2>&1; echo "rc=$?" >> $L; }
+run python -m pytest tests/test_gpu_parity.py -q
+for dt in fp32 bf16; do
+  run python tools/r2_probe.py time 8 64 512 97 97 $dt
+  run python tools/r2_probe.py time 8 64 512 129 129 $dt
+done
+run python tools/r2_probe.py time 8 64 512 193 193 fp32
+run python tools/r2_probe.py time 8 64 512 65 65 fp32
+grep -E "^\{\"mode|rc=|==|passed|failed|Error" $L | cut -c1-400
+CCA_B200_LIB=$PWD/ccnet_b200/lib_tl/libcca_b200.so timeout 300 python tools/r2_timeline.py fp32 >> gpurun_out/stage10.log 2>&1

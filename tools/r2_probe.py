@@ -62,6 +62,7 @@ def main():
                 fn()
             for _ in range(iters):
                 flush.zero_()
+                torch.cuda._sleep(300000)      # GPU spin while the host enqueues the op's launches (no host latency in the events)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 fn()

@@ -18,12 +18,12 @@ for _ in range(3):
     out, lse = cca_forward(q, k, v, impl="tc")
     cca_backward(do, q, k, v, out, lse, impl="tc")
 res = {}
-for name, hook in (("fwd", "cca_b200__set_debug_buffer"), ("bwd", "cca_b200__set_bwd_debug_buffer")):
+for name, hook in (("stats", "cca_b200__set_stats_debug_buffer"), ("fwd", "cca_b200__set_debug_buffer"), ("bwd", "cca_b200__set_bwd_debug_buffer")):
     fn = getattr(lib, hook)
     fn.argtypes = [ctypes.c_void_p]; fn.restype = None
     buf = torch.zeros(5 * 512, dtype=torch.int64, device=dev)
     fn(buf.data_ptr())
-    if name == "fwd":
+    if name in ("fwd", "stats"):
         cca_forward(q, k, v, impl="tc")
     else:
         cca_backward(do, q, k, v, out, lse, impl="tc")
