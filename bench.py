@@ -388,7 +388,8 @@ def run_ours(args):
     # ---- module level: resident and e2e (host buffers) -----------------------------------------------
     ms_mod = max_over_ranks(time_events(step_resident, max(3, args.steps // 2), 3, barrier))
     module = {"value": px / (ms_mod * 1e-3), "unit": UNIT, "ms_per_step": ms_mod,
-              "note": "CrissCrossAttention nn.Module x R fwd+bwd, x resident; includes the stock-torch fp32 1x1 convs"}
+              "note": "CrissCrossAttention nn.Module x R fwd+bwd, x resident (NCHW in, converted once per call); projections, "
+                      "attention and their backward all on this repository's tcgen05 kernels (one autograd node per step)"}
     ms_e2e_serial = max_over_ranks(time_events(step_e2e, max(3, args.steps // 2), 3, barrier))
     ms_e2e = max_over_ranks(time_events(step_e2e_pipelined, max(6, args.steps // 2), 4, barrier, finish=join_streams))
     e2e = {"value": px / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
@@ -396,7 +397,10 @@ def run_ours(args):
            "serial_ms_per_step": ms_e2e_serial, "serial_value": px / (ms_e2e_serial * 1e-3),
            "note": "nn.Module x R fwd+bwd; every step copies its x from pinned host memory and its y and dx back to pinned "
                    "host memory inside the timed region; value: copies on side streams overlapped with the neighbouring "
-                   "steps' compute (double-buffered); serial_*: the same step with copy -> compute -> copy -> sync in sequence"}
+                   "steps' compute (double-buffered); serial_*: the same step with copy -> compute -> copy -> sync in sequence",
+           "bound": "host link: %.0f MB out + %.0f MB in per step per GPU; at N GPUs the ranks share the host's memory / PCIe "
+                    "bandwidth (each rank is bound to its GPU's NUMA node)" % (2 * x_host.numel() * esize / 1e6, x_host.numel() * esize / 1e6),
+           "d2h_gbs": 2 * x_host.numel() * esize / (ms_e2e * 1e-3) / 1e9}
 
     # ---- per-op timings of the kernels of this repo -> roofline ----------------------------------------
     out, lse = cca_forward(q, k, v, impl=args.kernels)

@@ -36,7 +36,7 @@ using namespace tc;
 
 constexpr int kTmemCols = 512;      // S / dP double buffer: [0,128) [128,256)   O0: [256,320)   O1: [320,384)
 constexpr int kTmemO = 256;
-constexpr int kRegsSoft = 104, kRegsEpi = 128, kRegsConvB = 88;
+constexpr int kRegsSoft = 104, kRegsEpi = 128, kRegsConvB = 48;
 static_assert(reg_pool_ok(kRegsSoft, kRegsEpi, kRegsConvB), "setmaxnreg pool");
 constexpr int kZeroBuf = 2048;
 
@@ -80,9 +80,9 @@ template <int LK, bool BF> struct BwdSmem {
     static constexpr int off_p = off_out + kNOut * T::kSlot; // P / dS planes (hi, lo); M=128 over-reads of a slot land in the next slot / here
     static constexpr int off_tail = off_p + T::kP + (16 - LK / 8) * T::kPlane;   // pad for the P^T over-read (16 planes of 8 key pixels)
     static constexpr int off_zero = off_tail + (128 - LK) * 16 + 256;            // zero tile of the zero-ahead copies
-    static constexpr int off_dpart = off_zero + kZeroBuf;  // float [2][128]: per-pixel delta halves from the converters, then
+    static constexpr int off_dpart = off_zero + kZeroBuf;  // float [4][128]: per-pixel delta quarters from the converters, then
                                                            // unsigned [8]: readers of an O slot (one counter per ring slot)
-    static constexpr int off_bar = off_dpart + 1024 + 32;
+    static constexpr int off_bar = off_dpart + 2048 + 32;
     static constexpr int kBytes = off_bar + 8 * 48 + 32;
     static_assert(kBytes <= 232448, "shared memory budget");
 };
@@ -94,31 +94,32 @@ enum { B_LD_FULL = 0, B_LD_EMPTY = 6, B_OP_FULL = 12, B_S_FULL = 18, B_S_EMPTY =
 // does this item compute delta itself (its ring carries the O chunks)?
 __device__ __forceinline__ bool calc_delta(const BwdParams &p, const Item &it) { return p.delta_mode == 0 || (it.col && it.ik == 0); }
 
-// Converter step for a (dO, O) pair of ring slots: returns this thread's part of sum_c dO[r][c] * O[r][c] over its 32 channels of
-// the chunk and (fp32) rewrites the dO slot in place as bf16 hi/lo planes (layout of convert_slot_inplace: two independent
-// groups of 128 threads, one per 32-channel box).  The O slot goes back to the producer once BOTH groups have read it: the
-// second group leader to bump o_cnt arrives on the slot's LD_EMPTY barrier.
+// Converter step for a (dO, O) pair of ring slots: returns this thread's part of sum_c dO[r][c] * O[r][c] over its 16 channels of
+// the chunk and (fp32) rewrites the dO slot in place as bf16 hi/lo planes (layout and thread mapping of convert_slot_inplace: two
+// independent groups of 256 threads, one per 32-channel box; thread = (pixel row, 16-channel half)).  The O slot goes back to the
+// producer once BOTH groups have read it: the second group leader to bump o_cnt arrives on the slot's LD_EMPTY barrier.
 template <int LK, bool BF>
 __device__ __forceinline__ float convert_dot(uint8_t *dslot, const uint8_t *oslot, int t, uint64_t *o_empty, unsigned int *o_cnt)
 {
     using T = Tiles<LK, BF>;
-    const int r = t & 127, grp = t >> 7;
+    const int grp = t >> 8, r = t & 127, hq = (t >> 7) & 1;
     const int rr = r < LK ? r : LK - 1;
     const int sw = rr & 7;
     float acc = 0.f;
     auto group_sync_and_release = [&]() {
-        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-        else asm volatile("bar.sync 3, 128;" ::: "memory");
-        if (r == 0 && atomicAdd(o_cnt, 1u) == 1u) {       // both groups have read the O tile
+        if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+        else asm volatile("bar.sync 3, 256;" ::: "memory");
+        if ((t & 255) == 0 && atomicAdd(o_cnt, 1u) == 1u) {    // both groups have read the O tile
             *o_cnt = 0u;
             mbar_arrive(o_empty);
         }
     };
     if constexpr (BF) {
+        // one 128-byte-wide tile = 64 bf16 channels: 8 chunks of 16 B; this thread takes chunks 2*(2*grp + hq), +1
         const uint8_t *a = dslot + rr * 128, *b = oslot + rr * 128;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int j = grp * 4 + i;
+        for (int i = 0; i < 2; ++i) {
+            const int j = (grp * 2 + hq) * 2 + i;
             const uint4 x = *reinterpret_cast<const uint4 *>(a + ((j ^ sw) * 16));
             const uint4 y = *reinterpret_cast<const uint4 *>(b + ((j ^ sw) * 16));
             const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
@@ -127,22 +128,22 @@ __device__ __forceinline__ float convert_dot(uint8_t *dslot, const uint8_t *oslo
         }
         group_sync_and_release();
     } else {
-        float4 raw[8];
+        float4 raw[4];
         uint8_t *box = dslot + grp * T::kTile;
         const uint8_t *src = box + rr * 128;
         const uint8_t *osrc = oslot + grp * T::kTile + rr * 128;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) raw[j] = *reinterpret_cast<const float4 *>(src + ((j ^ sw) * 16));
+        for (int j = 0; j < 4; ++j) raw[j] = *reinterpret_cast<const float4 *>(src + (((hq * 4 + j) ^ sw) * 16));
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float4 o = *reinterpret_cast<const float4 *>(osrc + ((j ^ sw) * 16));
+        for (int j = 0; j < 4; ++j) {
+            const float4 o = *reinterpret_cast<const float4 *>(osrc + (((hq * 4 + j) ^ sw) * 16));
             acc += raw[j].x * o.x + raw[j].y * o.y + raw[j].z * o.z + raw[j].w * o.w;
         }
         group_sync_and_release();
         if (r < LK) {
-            uint8_t *d = box + r * 16;
+            uint8_t *d = box + r * 16 + hq * 2 * T::kPStride;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 2; ++j) {
                 const float4 a = raw[2 * j], b = raw[2 * j + 1];
                 const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
                 uint4 hi, lo;
@@ -179,7 +180,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S::off_bar);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::off_bar + 8 * B_COUNT);
     float *dpart = reinterpret_cast<float *>(smem + S::off_dpart);
-    unsigned int *o_cnt = reinterpret_cast<unsigned int *>(smem + S::off_dpart + 1024);
+    unsigned int *o_cnt = reinterpret_cast<unsigned int *>(smem + S::off_dpart + 2048);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NCH = p.C / kNC;
     const int KQ = p.Cq / 16;
@@ -441,7 +442,6 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
         uint32_t g = 0, ncalc = 0;
         // every ring slot passes through the converters (bf16 tiles only for the hand-shake: OP_FULL is what the MMA warp
         // waits for in both dtypes, so a slot the converters read for delta is never released before they are done).
-        // A converted slot is fenced + published only after the NEXT slot's loads have been issued (see convert_slot_inplace).
         uint32_t pend = 0;                                             // bit s: slot s converted, not yet published
         auto publish = [&]() {
             if (pend) {
@@ -464,8 +464,9 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                 wait_full(g);
                 CCA_STAMP(1);
                 if constexpr (!BF) {
-                    convert_slot_inplace<LK>(smem + S::off_ld + slot * T::kSlot, t, publish);
+                    convert_slot_inplace<LK>(smem + S::off_ld + slot * T::kSlot, t);
                     pend |= 1u << slot;
+                    publish();                                         // (deferring it past the next slot's loads cost 7 % here)
                 } else {
                     mbar_arrive(&bars[B_OP_FULL + slot]);              // bf16: nothing to convert, nothing to fence
                 }
@@ -487,6 +488,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                                                 o_cnt + so);
                     if constexpr (!BF) {
                         pend |= (1u << sd) | (1u << so);               // (nobody waits for the O slot; keeps its phase in step)
+                        publish();
                     } else {
                         mbar_arrive(&bars[B_OP_FULL + sd]);
                         mbar_arrive(&bars[B_OP_FULL + so]);
@@ -499,7 +501,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             if (calc) {                                                // hand the per-pixel sums to the P/dS group
                 publish();                                             // (never block on anything but a load with a slot withheld)
                 mbar_wait(&bars[B_DELTA_EMPTY], (ncalc & 1) ^ 1);
-                dpart[(t >> 7) * 128 + (t & 127)] = dacc;
+                dpart[(t >> 7) * 128 + (t & 127)] = dacc;          // (t >> 7) = 2 * group + channel half
                 mbar_arrive(&bars[B_DELTA_FULL]);
                 ++ncalc;
             }
@@ -580,7 +582,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
             float dl = 0.f;
             if (calc) {
                 mbar_wait(&bars[B_DELTA_FULL], ncalc & 1);
-                dl = dpart[r] + dpart[128 + r];
+                dl = (dpart[r] + dpart[128 + r]) + (dpart[256 + r] + dpart[384 + r]);
                 mbar_arrive(&bars[B_DELTA_EMPTY]);
                 ++ncalc;
                 // delta[B,H,W] always ends up in the workspace (the caller's d gamma = sum of it); in mode 1 it is also how the

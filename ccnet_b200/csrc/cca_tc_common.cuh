@@ -13,24 +13,26 @@ constexpr int kNC = 64;   // channels per chunk (one ring slot = [LK px][64 ch] 
 constexpr uint32_t kSw128 = 2;   // UMMA smem-descriptor layout type SWIZZLE_128B: a bf16 TMA tile [rows][128 B] is directly a
                                  // K-major operand (rows = M/N, k-step = +32 B) or an MN-major one (rows = K, k-step = +2048 B)
 
-// Thread layout of both kernels (five warpgroups, registers rebalanced with setmaxnreg):
-//   warps 0-3   (128 thr) : epilogue group        (TMEM lane == pixel; accumulators -> staging -> TMA store)
+// Thread layout of the kernels (seven warpgroups, registers rebalanced with setmaxnreg):
+//   warps 0-3   (128 thr) : epilogue group        (TMEM lane == pixel; accumulators -> staging)
 //   warps 4-7   (128 thr) : softmax / P / dS group (TMEM lane == pixel)
-//   warps 8-15  (256 thr) : converters -- fp32 staging tile -> bf16 hi/lo operand planes
-//   warp 16               : TMA producer (one elected lane)
-//   warp 17               : MMA issuer (whole warp converged, tcgen05.mma under elect.sync)
-//   warp 18               : store warp (one lane): staging slots <-> global (TMA stores, partial prefetch, publishing)
-//   warp 19               : idle (pads the last warpgroup so setmaxnreg can release its registers)
-constexpr int kThreads = 640;
-constexpr int kConvThreads = 256;
-constexpr int kWarpConv0 = 8, kWarpProducer = 16, kWarpMma = 17, kWarpStore = 18;
-constexpr int kRegsMisc = 72;
+//   warps 8-23  (512 thr) : converters -- fp32 staging tile -> bf16 hi/lo operand planes.  The conversion is ~1200 warp
+//                           instructions per 28 KB slot and a slot used to take ~1000 cycles with 8 warps (two per scheduler,
+//                           mostly waiting on their own dependent instructions), which paced every fp32 chunk; 16 warps
+//                           halve the work per warp and double the warps a scheduler can pick from.
+//   warp 24               : TMA producer (one elected lane)
+//   warp 25               : MMA issuer (whole warp converged, tcgen05.mma under elect.sync)
+//   warps 26, 27          : store warps (one lane each, alternating items): staging slots -> global, counters
+constexpr int kThreads = 896;
+constexpr int kConvThreads = 512;
+constexpr int kWarpConv0 = 8, kWarpProducer = 24, kWarpMma = 25, kWarpStore = 26;
+constexpr int kRegsLaunch = 72;           // 65536 / 896 rounded down to a multiple of 8
+constexpr int kRegsMisc = 56;
 // setmaxnreg moves registers through a per-CTA pool that only holds what the CTA itself released: the increases must be
-// covered by the decreases relative to the launch allocation of 96 regs/thread (640 threads):
-//   released 256*(96-88) + 128*(96-72) = 5120  >=  claimed 128*(104-96) + 128*(128-96) = 5120   (both kernels)
+// covered by the decreases relative to the launch allocation (kRegsLaunch per thread).
 constexpr bool reg_pool_ok(int soft, int epi, int conv)
 {
-    return 256 * (96 - conv) + 128 * (96 - kRegsMisc) >= 128 * (soft - 96) + 128 * (epi - 96);
+    return kConvThreads * (kRegsLaunch - conv) + 128 * (kRegsLaunch - kRegsMisc) >= 128 * (soft - kRegsLaunch) + 128 * (epi - kRegsLaunch);
 }
 
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -90,34 +92,31 @@ __device__ __forceinline__ bool elect_one()
 
 // Converter: one staged slot ([LK px][64 ch] fp32 as two swizzled 32-channel TMA boxes) -> bf16 hi/lo operand planes
 // [8-channel chunk][pixel][16 B], IN PLACE.  Each box is rewritten inside its own bytes (planes hi0 lo0 .. hi3 lo3 of its 32
-// channels take exactly the box's LK x 128 B), so the two boxes are handled by two independent groups of 128 threads (group =
-// t >> 7, one thread per pixel row): every thread reads and splits its 128 B, the group meets on its own named barrier (1 or
-// 3), then overwrites.  The groups drift apart, which overlaps one group's shared-memory phase with the other's ALU phase.
-// `mid` runs after the loads have been issued and before the group barrier: the callers use it to fence + publish the PREVIOUS
-// slot there, so that the proxy fence (which waits for the thread's outstanding shared-memory stores to drain, a few hundred
-// cycles right after 8 STS.128) overlaps the load latency of this slot instead of sitting on the critical path.
+// channels take exactly the box's LK x 128 B), so the two boxes are handled by two independent groups of 256 threads (group =
+// t >> 8; inside a group thread = (pixel row, 16-channel half)): every thread reads and splits its 64 B, the group meets on its
+// own named barrier (1 or 3), then overwrites.  `mid` runs after the loads have been issued and before the group barrier.
 struct ConvertNoMid { __device__ __forceinline__ void operator()() const {} };
 template <int LK, typename Mid = ConvertNoMid>
 __device__ __forceinline__ void convert_slot_inplace(uint8_t *slot, int t, Mid mid = Mid())
 {
     using T = Tiles<LK, false>;
-    const int r = t & 127, grp = t >> 7;
+    const int grp = t >> 8, r = t & 127, hq = (t >> 7) & 1;
     uint8_t *box = slot + grp * T::kTile;
-    float4 raw[8];                                              // the thread's 32 channels; split only after the barrier (fewer live registers)
+    float4 raw[4];                                              // the thread's 16 channels
     {
         const int rr = r < LK ? r : LK - 1;                     // idle threads re-read the last row (unconditional loads keep raw[] in registers)
         const uint8_t *src = box + rr * 128;
         const int sw = rr & 7;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) raw[j] = *reinterpret_cast<const float4 *>(src + ((j ^ sw) * 16));
+        for (int j = 0; j < 4; ++j) raw[j] = *reinterpret_cast<const float4 *>(src + (((hq * 4 + j) ^ sw) * 16));
     }
     mid();
-    if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-    else asm volatile("bar.sync 3, 128;" ::: "memory");
+    if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+    else asm volatile("bar.sync 3, 256;" ::: "memory");
     if (r < LK) {
-        uint8_t *d = box + r * 16;
+        uint8_t *d = box + r * 16 + hq * 2 * T::kPStride;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 2; ++j) {
             const float4 a = raw[2 * j], b = raw[2 * j + 1];
             const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
             uint4 hi, lo;

@@ -44,7 +44,7 @@ using namespace tc;
 
 constexpr int kTmemCols = 512;      // S [0,128)   P double buffer (hi/lo) [128,256) [256,384)   O ring 2 x 64 [384,512)
 constexpr int kTmemP = 128, kTmemO = 384, kNOB = 2;
-constexpr int kRegsSoft = 104, kRegsEpi = 128, kRegsConvF = 88;
+constexpr int kRegsSoft = 104, kRegsEpi = 128, kRegsConvF = 48;
 static_assert(reg_pool_ok(kRegsSoft, kRegsEpi, kRegsConvF), "setmaxnreg pool");
 constexpr int kNOutMax = 4;         // staging slots: 2 (fp32: shared memory is full) or 4 (bf16: 14 KB each; the store path -- one TMA
                                     // instruction per chunk, ~500 cycles until the tile has left shared memory -- needs the slack)
