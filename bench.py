@@ -58,15 +58,10 @@ def bind_to_gpu_numa_node(local_rank: int):
     capped the end-to-end curve at 8 GPUs in round 1 (GPUs 4-7 sit on NUMA node 1)."""
     info = {"numa_node": None, "cpus": None}
     try:
-        import torch
-        bdf = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
-    except Exception:
-        bdf = None
-    try:
-        if bdf is None:
-            out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
-                                 capture_output=True, text=True, timeout=10).stdout.strip()
-            bdf = out
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = vis.split(",")[local_rank].strip() if vis else str(local_rank)      # nvidia-smi indexes physical devices
+        bdf = subprocess.run(["nvidia-smi", "-i", phys, "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip()
         bdf = bdf.lower()
         if len(bdf.split(":")[0]) == 8:                    # nvidia-smi prints an 8-digit domain, sysfs a 4-digit one
             bdf = bdf[4:]

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-L=gpurun_out/stage11.log
+L=gpurun_out/stage13.log
 : > $L
 run() { echo "== $*" >> $L; timeout 600 "$@" >> $L 2>&1; echo "rc=$?" >> $L; }
 for dt in fp32 bf16; do
