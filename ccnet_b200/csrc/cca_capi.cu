@@ -61,13 +61,13 @@ int tc_pdl() { return knob(g_pdl, "CCA_B200_PDL", 1, 0, 1); }
 int tc_zero_ahead() { return knob(g_zero_ahead, "CCA_B200_ZERO_AHEAD", 1, 1, 4); }
 int tc_delta_mode() { return knob(g_delta, "CCA_B200_DELTA", -1, -1, 1); }
 int tc_lag() { return knob(g_lag, "CCA_B200_LAG", -1, -1, 1); }
-int tc_l2_hints() { return knob(g_hints, "CCA_B200_L2HINT", 1, 0, 1); }
+int tc_l2_hints() { return knob(g_hints, "CCA_B200_L2HINT", 1, 0, 2); }
 #ifdef CCA_DEBUG_HOOKS
 void set_tc_pdl(int on) { g_pdl.store(on ? 1 : 0); }
 void set_tc_zero_ahead(int n) { g_zero_ahead.store(n < 1 ? 1 : (n > 4 ? 4 : n)); }
 void set_tc_delta_mode(int m) { g_delta.store(m < -1 || m > 1 ? -1 : m); }
 void set_tc_lag(int v) { g_lag.store(v < -1 || v > 1 ? -1 : v); }
-void set_tc_l2_hints(int v) { g_hints.store(v ? 1 : 0); }
+void set_tc_l2_hints(int v) { g_hints.store(v < 0 || v > 2 ? 1 : v); }
 #endif
 }  // namespace cca
 

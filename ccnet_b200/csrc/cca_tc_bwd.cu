@@ -231,8 +231,8 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                     CCA_STAMP(0);
                     uint8_t *dst = smem + S::off_ld + slot * T::kSlot;
                     mbar_expect_tx(&bars[B_LD_FULL + slot], T::kSlot);
-                    if (p.hints) {          // what the sample's consumers read again stays; O and the consumers' own operands stream
-                        const uint64_t pol = (is_producer(it) && !last_use) ? pol_keep : pol_stream;
+                    if (p.hints == 1) {     // what the sample's consumers read again stays; O and the consumers' own operands stream
+                        const uint64_t pol = (is_producer(it) && !last_use) ? pol_keep : pol_stream;   // (hints == 2: keep outputs only)
                         tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, it.b, pol);
                         if constexpr (!BF) tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, it.b, pol);
                     } else {

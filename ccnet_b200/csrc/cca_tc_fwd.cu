@@ -145,7 +145,9 @@ cca_tc_fwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                     CCA_STAMP(0);
                     uint8_t *dst = smem + S::off_ld + slot * T::kSlot;
                     mbar_expect_tx(&bars[B_LD_FULL + slot], T::kSlot);
-                    if (p.hints) {          // producers' operands are read again by the sample's consumers; theirs are not
+                    if (p.hints == 1) {     // producers' operands are read again by the sample's consumers; theirs are not
+                        // (hints == 2: no hints on the loads, only the output tiles are kept -- a reduce-add that misses L2 costs a
+                        //  DRAM read-modify-write at 2.4 TB/s, an operand re-read that misses is a plain read)
                         const uint64_t pol = is_producer(it) ? pol_keep : pol_stream;
                         tma_load_4d(dst, m, &bars[B_LD_FULL + slot], c0, cw, ch, it.b, pol);
                         if constexpr (!BF) tma_load_4d(dst + T::kTile, m, &bars[B_LD_FULL + slot], c0 + 32, cw, ch, it.b, pol);

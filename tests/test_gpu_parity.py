@@ -180,7 +180,7 @@ def test_launch_knobs_are_bit_identical(dtype):
     dt = torch.float32 if dtype == "fp32" else torch.bfloat16
     cl = torch.channels_last
     # (pdl, delta mode, lag, hints)
-    combos = [(1, -1, -1, 1)] if pdl is None else [(1, -1, -1, 1), (0, -1, -1, 1), (1, 0, 0, 1), (1, 1, 1, 0), (0, 0, 1, 1), (1, 1, 0, 0)]
+    combos = [(1, -1, -1, 1)] if pdl is None else [(1, -1, -1, 1), (0, -1, -1, 1), (1, 0, 0, 1), (1, 1, 1, 0), (0, 0, 1, 2), (1, 1, 0, 0)]
     for shape in [(8, 64, 512, 97, 97), (2, 32, 256, 20, 97), (5, 16, 64, 7, 3)]:
         q, k, v = _rand_qkv(*shape, seed=5 + sum(shape))
         q, k, v = (t.to(dev).to(dt).contiguous(memory_format=cl) for t in (q, k, v))
