@@ -478,8 +478,12 @@ def run_ours(args):
                              "convolutions = torch default), DDP + SyncBatchNorm when N > 1, per-GPU batch = 8 / N (engine.py:88); "
                              "cca_modules_ms = the R criss-cross modules alone (projection GEMMs + operator + residual, fwd+bwd) "
                              "at the head's feature-map size")
+            if world == 1:                            # evaluate.py's loop on one synthetic Cityscapes-sized image (8 windows of 769^2)
+                torch.cuda.empty_cache()
+                from harness.eval_synth import run as eval_run
+                ccnet["eval"] = eval_run(local_rank, steps=1, warmup=1)
         except Exception as exc:                      # never lose the main line to the extra leg
-            ccnet = {"error": repr(exc)[:300]}
+            ccnet = (ccnet or {}) | {"error": repr(exc)[:300]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

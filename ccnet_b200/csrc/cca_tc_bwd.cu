@@ -34,8 +34,8 @@ namespace cca {
 namespace {
 using namespace tc;
 
-constexpr int kTmemCols = 512;      // S / dP double buffer: [0,128) [128,256)   O0: [256,320)   O1: [320,384)
-constexpr int kTmemO = 256;
+constexpr int kTmemCols = 512;      // S / dP double buffer: [0,128) [128,256)   dV ring O0: [256,320) O1: [320,384)   dQ: [384,448)   dK: [448,512)
+constexpr int kTmemO = 256, kTmemQK = 384;   // dQ / dK have accumulators of their own: phase D never waits for the dV tiles to drain
 constexpr int kRegsSoft = 104, kRegsEpi = 128, kRegsConvB = 48;
 static_assert(reg_pool_ok(kRegsSoft, kRegsEpi, kRegsConvB), "setmaxnreg pool");
 constexpr int kZeroBuf = 2048;
@@ -89,7 +89,8 @@ template <int LK, bool BF> struct BwdSmem {
 
 enum { B_LD_FULL = 0, B_LD_EMPTY = 6, B_OP_FULL = 12, B_S_FULL = 18, B_S_EMPTY = 20, B_P_FULL = 22,
        B_P_EMPTY = 23, B_O_FULL = 24, B_O_EMPTY = 26, B_OUT_FULL = 28, B_STAGED = 29, B_DP_FULL = 30, B_DS_FULL = 31,
-       B_DELTA_FULL = 32, B_DELTA_EMPTY = 33, B_OUT_FREE = 34, B_STAGED_W = 37, B_COUNT = 43 };   // B_OUT_FREE[slot], B_STAGED_W[store warp][slot]
+       B_DELTA_FULL = 32, B_DELTA_EMPTY = 33, B_OUT_FREE = 34, B_STAGED_W = 37, B_QK_FULL = 43, B_QK_EMPTY = 45,
+       B_COUNT = 47 };   // B_OUT_FREE[slot], B_STAGED_W[store warp][slot], B_QK_*[dQ, dK]
 
 // does this item compute delta itself (its ring carries the O chunks)?
 __device__ __forceinline__ bool calc_delta(const BwdParams &p, const Item &it) { return p.delta_mode == 0 || (it.col && it.ik == 0); }
@@ -195,6 +196,7 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
         for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_O_FULL + i], 1); mbar_init(&bars[B_O_EMPTY + i], 128); }
         for (int i = 0; i < 3; ++i) { mbar_init(&bars[B_OUT_FREE + i], 1); mbar_init(&bars[B_STAGED_W + i], 128); mbar_init(&bars[B_STAGED_W + 3 + i], 128); }
         for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_S_FULL + i], 1); mbar_init(&bars[B_S_EMPTY + i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_QK_FULL + i], 1); mbar_init(&bars[B_QK_EMPTY + i], 128); }
         mbar_init(&bars[B_P_FULL], 128); mbar_init(&bars[B_P_EMPTY], 1);
         mbar_init(&bars[B_DP_FULL], 1);  mbar_init(&bars[B_DS_FULL], 128);
         mbar_init(&bars[B_DELTA_FULL], kConvThreads); mbar_init(&bars[B_DELTA_EMPTY], 128);
@@ -333,20 +335,17 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
                 {
                     const uint32_t q = opb(u), kk = opb(u + 1);
                     wait_op(u); wait_op(u + 1);
-                    mbar_wait(&bars[B_O_EMPTY + (oc & 1)], ((oc >> 1) & 1) ^ 1);
+                    mbar_wait(&bars[B_QK_EMPTY + 0], (k & 1) ^ 1);
+                    mbar_wait(&bars[B_QK_EMPTY + 1], (k & 1) ^ 1);
                     tc_fence_after();
-                    mma_split3_loop<LK / 16, TERMS>(tmem + kTmemO + (oc & 1) * kNC, pb, pb + LOP, 2 * T::kPlane, T::kPlane, 128,
+                    mma_split3_loop<LK / 16, TERMS>(tmem + kTmemQK, pb, pb + LOP, 2 * T::kPlane, T::kPlane, 128,
                                                     kk, kk + LO8, KS_MN, LBO_MN, SBO_MN, id_k_mn, false, 0, LAY);
-                    commit_to(&bars[B_O_FULL + (oc & 1)]);
+                    commit_to(&bars[B_QK_FULL + 0]);
                     free_op(u + 1);
-                    ++oc;
-                    mbar_wait(&bars[B_O_EMPTY + (oc & 1)], ((oc >> 1) & 1) ^ 1);
-                    tc_fence_after();
-                    mma_split3_loop<LK / 16, TERMS>(tmem + kTmemO + (oc & 1) * kNC, pb, pb + LOP, 256, 128, T::kPlane,
+                    mma_split3_loop<LK / 16, TERMS>(tmem + kTmemQK + kNC, pb, pb + LOP, 256, 128, T::kPlane,
                                                     q, q + LO8, KS_MN, LBO_MN, SBO_MN, id_mn_mn, false, 0, LAY);
-                    commit_to(&bars[B_O_FULL + (oc & 1)]);
+                    commit_to(&bars[B_QK_FULL + 1]);
                     free_op(u);
-                    ++oc;
                     commit_to(&bars[B_P_EMPTY]);
                     u += 2;
                 }
@@ -646,25 +645,29 @@ cca_tc_bwd_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant
         reg_inc<kRegsEpi>();
         const int r = tid;
         const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
-        uint32_t oc = 0;
+        uint32_t oc = 0, nt = 0;                              // dV accumulators consumed, tiles staged
         int dbg_n = tid == 0 ? 0 : 512;
         (void)dbg_n;
         for (int k = 0; k < nk; ++k) {
-            for (int i = 0; i < NO; ++i, ++oc) {
+            for (int i = 0; i < NO; ++i, ++nt) {
+                const bool qk = i >= NCH;                     // dQ (i == NCH), dK (NCH + 1): accumulators of their own
                 const int ob = oc & 1;
-                const int os = oc % kNOut;
+                const int os = nt % kNOut;
                 uint8_t *slot = smem + S::off_out + os * T::kSlot;
                 CCA_STAMP(4);
-                mbar_wait(&bars[B_OUT_FREE + os], ((oc / kNOut) & 1) ^ 1);   // the store of tile oc - kNOut has left the slot
-                mbar_wait(&bars[B_O_FULL + ob], (oc >> 1) & 1);
+                mbar_wait(&bars[B_OUT_FREE + os], ((nt / kNOut) & 1) ^ 1);   // the store of tile nt - kNOut has left the slot
+                if (qk) mbar_wait(&bars[B_QK_FULL + (i - NCH)], k & 1);
+                else mbar_wait(&bars[B_O_FULL + ob], (oc >> 1) & 1);
                 tc_fence_after();
                 CCA_STAMP(4);
                 float o[kNC];
+                const uint32_t src = tl + (qk ? kTmemQK + (i - NCH) * kNC : kTmemO + ob * kNC);
 #pragma unroll
-                for (int c0 = 0; c0 < kNC; c0 += 16) tmem_ld16(tl + kTmemO + ob * kNC + c0, reinterpret_cast<uint32_t *>(o + c0));
+                for (int c0 = 0; c0 < kNC; c0 += 16) tmem_ld16(src + c0, reinterpret_cast<uint32_t *>(o + c0));
                 tmem_ld_wait();
                 tc_fence_before();
-                mbar_arrive(&bars[B_O_EMPTY + ob]);
+                if (qk) mbar_arrive(&bars[B_QK_EMPTY + (i - NCH)]);
+                else { mbar_arrive(&bars[B_O_EMPTY + ob]); ++oc; }
                 // rows beyond the tile are exact zeros (P and dS are zero there): inside the image they add nothing, outside the
                 // TMA clips them
                 if (r < LK) {
