@@ -198,6 +198,18 @@ template <int N> __device__ __forceinline__ void tma_store_wait_all()
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---------------------------------------------------------------- plain global stores / reductions with an L2 eviction hint
+__device__ __forceinline__ void st_global_f32(float *p, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ void st_global_f32(float *p, float v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_global_add_f32(float *p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ void red_global_add_f32(float *p, float v, uint64_t pol)
+{
+    asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 template <int NCOLS> __device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst)
 {
@@ -249,6 +261,15 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *r)
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t *r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, const uint32_t *r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(r[0]), "r"(r[1]) : "memory");
 }
 // wait::ld that also "produces" the 16 registers of an earlier tmem_ld16: the compiler cannot move a use of r[] above it,
 // so a load may be issued ahead of the code that overlaps its latency
