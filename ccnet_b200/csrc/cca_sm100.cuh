@@ -204,6 +204,15 @@ __device__ __forceinline__ void st_global_f32(float *p, float v, uint64_t pol)
 {
     asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
 }
+// byte-address forms (a running 64-bit address costs two integer instructions per store; a float index costs four)
+__device__ __forceinline__ void st_global_f32(uint64_t a, float v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(a), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_global_add_f32(uint64_t a, float v, uint64_t pol)
+{
+    asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(a), "f"(v), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void red_global_add_f32(float *p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 __device__ __forceinline__ void red_global_add_f32(float *p, float v, uint64_t pol)
 {

@@ -40,10 +40,16 @@ namespace cca {
 namespace {
 using namespace tc;
 
-constexpr int kRegsSoftT = 104, kRegsEpiT = 88, kRegsConvT = 64;
-static_assert(reg_pool_ok(kRegsSoftT, kRegsEpiT, kRegsConvT), "setmaxnreg pool");
 constexpr int kGroupCh = 128;       // channels per accumulator group (= TMEM lanes)
-constexpr int kNA = 64;             // columns (query pixels) of the first accumulator half
+constexpr int kNA = 48;             // columns (query pixels) of the first accumulator half (the second one has LK - 48)
+constexpr int kThreadsT = 1024;     // 32 warps: the 28 of cca_tc_common.cuh plus a second epilogue group (warps 28-31)
+constexpr int kRegsLaunchT = 64;    // 65536 / 1024
+constexpr int kWarpEpiB = 28;
+// register budget (setmaxnreg; launch allocation 64 per thread): the converters hold a 32-key column of their channel plus its
+// hi/lo split across a wait and get what the epilogue, producer, MMA and idle warps give up
+constexpr int kRegsSoftT = 72, kRegsEpiT = 56, kRegsConvT = 72, kRegsMiscT = 40;
+static_assert(256 * (kRegsLaunchT - kRegsEpiT) + 128 * (kRegsLaunchT - kRegsMiscT) >=
+              kConvThreads * (kRegsConvT - kRegsLaunchT) + 128 * (kRegsSoftT - kRegsLaunchT), "setmaxnreg pool");
 
 struct FwdTParams {
     ItemSpace sp;
@@ -78,7 +84,7 @@ enum { T_LD_FULL = 0, T_LD_EMPTY = 8, T_OP_FULL = 16, T_S_FULL = 24, T_S_EMPTY =
        T_V_FULL = 30, T_V_EMPTY = 32, T_O_FULL = 34, T_O_EMPTY = 36, T_COUNT = 38 };
 
 template <int LK>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsT, 1)
 cca_tc_fwdt_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constant__ CUtensorMap mqr,
                    const __grid_constant__ CUtensorMap mkc, const __grid_constant__ CUtensorMap mkr,
                    const __grid_constant__ CUtensorMap mvc, const __grid_constant__ CUtensorMap mvr, FwdTParams p)
@@ -87,7 +93,7 @@ cca_tc_fwdt_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constan
     using S = FwdTSmem<LK>;
     using TM = TmemT<LK>;
     constexpr int kNLd = S::kNLd;
-    constexpr int kNB = LK - kNA;             // columns of the second accumulator half (48 or 16)
+    constexpr int kNB = LK - kNA;             // columns of the second accumulator half (64 or 32)
     static_assert(LK % 16 == 0 && LK / 16 <= 8 && kNB % 16 == 0 && kNB >= 16, "tile geometry");
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S::off_bar);
@@ -122,8 +128,8 @@ cca_tc_fwdt_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constan
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp >= kWarpProducer) {
-        reg_dec<kRegsMisc>();
+    if (warp >= kWarpProducer && warp < kWarpEpiB) {
+        reg_dec<kRegsMiscT>();
         if (warp == kWarpProducer) {
             // =============================== TMA producer ===============================
             if (lane == 0) {
@@ -209,7 +215,7 @@ cca_tc_fwdt_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constan
                         if (elect_one()) {
                             const uint32_t d = tmem + TM::kO + hb * kNA;
                             const uint32_t idesc = hb ? idesc_b : idesc_a;
-                            const uint32_t prow = pb + hb * kNA * 16;                    // query rows [0, 64) or [64, LK) of every plane
+                            const uint32_t prow = pb + hb * kNA * 16;                    // query rows [0, 48) or [48, LK) of every plane
 #pragma unroll
                             for (int ks = 0; ks < LK / 16; ++ks) {
                                 const uint64_t bh = smem_desc(prow + ks * 2 * T::kPlane, T::kPlane, 128);
@@ -228,9 +234,9 @@ cca_tc_fwdt_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constan
             }
         }
         // (warps 26, 27 have no role in this kernel)
-    } else if (warp >= kWarpConv0) {
+    } else if (warp >= kWarpConv0 && warp < kWarpEpiB) {
         // =============================== converters (512 threads) ===============================
-        reg_dec<kRegsConvT>();
+        reg_inc<kRegsConvT>();
         const int t = tid - kWarpConv0 * 32;
         const int quarter = warp & 3;                              // TMEM lane quarter this warp may access
         const int half = quarter >> 1, box = quarter & 1;          // chunk parity it serves, 32-channel TMA box inside the chunk
@@ -267,15 +273,31 @@ cca_tc_fwdt_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constan
             const int slot = g % kNLd;
             if ((n & 1) == half) {
                 wait_full(slot, g);
-                // 16-key units of this warp (tcgen05.st column addresses stay multiples of 8): units [u0, u0 + nu)
-                const uint8_t *src = smem + S::off_ld + slot * T::kSlot + box * T::kTile + (lane & 3) * 4 + u0 * 16 * 128;
-                float x[32];
+                // 16-key units of this warp (tcgen05.st column addresses stay multiples of 8): units [u0, u0 + nu).
+                // Row j of the swizzled tile keeps its 16-byte chunk c at ((c ^ (j & 7)) * 16) and (u0 * 16 + i) & 7 == i & 7.
+                // (bits 4-6 of `src` are exactly (lane >> 2) << 4: the chunk swizzle of row i is one XOR with a constant)
+                const uint32_t src = smem_u32(smem + S::off_ld + slot * T::kSlot + box * T::kTile) + u0 * 16 * 128 + (lane & 3) * 4 +
+                                     ((lane >> 2) << 4);
+                uint32_t hi[16], lo[16];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    // row j of the swizzled tile: the 16-byte chunk c of the row sits at ((c ^ (j & 7)) * 16); (u0 * 16 + i) & 7 == i & 7
-                    if (i < nu * 16) x[i] = *reinterpret_cast<const float *>(src + i * 128 + (((lane >> 2) ^ (i & 7)) << 4));
+                for (int uu = 0; uu < 2; ++uu) {
+                    if (uu < nu) {                              // one 16-key unit at a time: 16 loads in flight, then split
+                        float x[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[i]) : "r"((src ^ ((i & 7) << 4)) + (uu * 16 + i) * 128));
+                        if (uu == 0) publish();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) split2(x[2 * i], x[2 * i + 1], hi[8 * uu + i], lo[8 * uu + i]);
+                    }
                 }
-                publish();
+                // the slot goes back BEFORE the wait for the tensor-memory buffer: the registers are one more stage of prefetch
+                // (the ring is only kNLd slots deep and Q', K' of the next item hold two of them for a while)
+                __syncwarp();
+                if (lane == 0 && atomicAdd(&rd_cnt[slot], 1u) == 7u) {       // the 8 warps of this half have read the slot
+                    rd_cnt[slot] = 0u;
+                    mbar_arrive(&bars[T_LD_EMPTY + slot]);
+                }
                 const uint32_t vb = gcn & 1;
                 mbar_wait(&bars[T_V_EMPTY + vb], ((gcn >> 1) & 1) ^ 1);      // the MMAs of group gcn - 2 have read this buffer
                 tc_fence_after();
@@ -283,18 +305,9 @@ cca_tc_fwdt_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constan
 #pragma unroll
                 for (int uu = 0; uu < 2; ++uu) {
                     if (uu < nu) {
-                        uint32_t hi[8], lo[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) split2(x[16 * uu + 2 * i], x[16 * uu + 2 * i + 1], hi[i], lo[i]);
-                        tmem_st8(ch + uu * 8, hi);
-                        tmem_st8(cl + uu * 8, lo);
+                        tmem_st8(ch + uu * 8, hi + 8 * uu);
+                        tmem_st8(cl + uu * 8, lo + 8 * uu);
                     }
-                }
-                // the slot goes back to the producer once the 8 warps of this half have read it (the values are in registers)
-                __syncwarp();
-                if (lane == 0 && atomicAdd(&rd_cnt[slot], 1u) == 7u) {
-                    rd_cnt[slot] = 0u;
-                    mbar_arrive(&bars[T_LD_EMPTY + slot]);
                 }
                 tmem_st_wait();
                 tc_fence_before();
@@ -311,9 +324,9 @@ cca_tc_fwdt_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constan
                 if (n == NCH - 1) gcn += (uint32_t)NG;
             }
         publish();
-    } else if (warp >= 4) {
-        // =============================== softmax group (128 threads, TMEM lane == query pixel) ===============================
+    } else if (warp >= 4 && warp < kWarpEpiB) {
         reg_inc<kRegsSoftT>();
+        // =============================== softmax group (128 threads, TMEM lane == query pixel) ===============================
         const int r = tid - 128;
         const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         pdl_wait();                                                // parts come from the statistics kernel
@@ -369,67 +382,90 @@ cca_tc_fwdt_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_constan
             mbar_arrive(&bars[T_S_EMPTY]);
         }
     } else {
-        // =============================== epilogue group (128 threads, TMEM lane == channel of the group) ===============================
-        reg_inc<kRegsEpiT>();
-        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
-        const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+        // =============================== epilogue groups (2 x 128 threads, TMEM lane == channel of the group) ===============================
+        // Group A (warps 0-3) drains accumulator half a, group B (warps 28-31) half b.  ~220 four-byte stores per thread and item,
+        // each a warp-wide 128-byte line: what matters is the length of the dependent instruction chain of a warp, so the code is
+        // kept lean (16 columns at a time, the next 16 already in flight from tensor memory, two independent running addresses).
+        reg_dec<kRegsEpiT>();
+        const int hb = warp >= kWarpEpiB ? 1 : 0;
+        const int etid = (warp & 3) * 32 + lane;                   // TMEM lane = channel inside the 128-channel group
+        const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const int ncols = hb ? kNB : kNA, q0 = hb * kNA;
+        const uint32_t src = tl + TM::kO + q0;
+        const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first(), pol_normal = l2_policy_evict_normal();
         const bool one_tile = p.sp.col.nt == 1 && p.sp.row.nt == 1;
         uint32_t gc = 0;
         pdl_wait();                                                // statistics kernel complete: counters cleared, the output is ours
         for (int k = 0; k < nk; ++k) {
             const Item it = item_of(k);
             const bool prod = is_producer(it);
-            float *o0 = p.out + item_pixel(p.sp, it, 0) * (long)p.C + tid;     // query 0, channel `tid` of group 0
-            const long qstep = (long)(it.col ? p.sp.W : 1) * p.C;              // floats between consecutive query pixels
+            // producers' tiles are added onto by the sample's consumers: keep them in L2; a consumer's add is the last touch
+            const uint64_t pol = !p.hints ? pol_normal : (prod ? pol_keep : (one_tile ? pol_stream : pol_normal));
+            const uint64_t qb = (uint64_t)(it.col ? p.sp.W : 1) * p.C * 4;     // bytes between consecutive query pixels
+            // byte address of (query q0, channel etid of group 0)
+            const uint64_t o0 = reinterpret_cast<uint64_t>(p.out + item_pixel(p.sp, it, 0) * (long)p.C + etid) + (uint64_t)q0 * qb;
+            const int nq = it.lq - q0;                             // valid query pixels of this half (may be <= 0 or > ncols)
             bool waited = prod;
-            for (int g = 0; g < NG; ++g, ++gc) {
-                float *og = o0 + g * kGroupCh;
-#pragma unroll
-                for (int hb = 0; hb < 2; ++hb) {
-                    constexpr int kMaxCols = kNA;
-                    const int ncols = hb ? kNB : kNA;
-                    float o[kMaxCols];
-                    mbar_wait(&bars[T_O_FULL + hb], gc & 1);
-                    tc_fence_after();
-#pragma unroll
-                    for (int c0 = 0; c0 < kMaxCols; c0 += 16)
-                        if (c0 < ncols) tmem_ld16(tl + TM::kO + hb * kNA + c0, reinterpret_cast<uint32_t *>(o + c0));
-                    tmem_ld_wait();
-                    tc_fence_before();
-                    mbar_arrive(&bars[T_O_EMPTY + hb]);            // the accumulator half is in registers: the next group may overwrite it
-                    if (!waited) {                                 // every producer of this sample has stored its tile
-                        if (tid == 0) wait_count(p.cdone + it.b, (unsigned)p.sp.seg0);
-                        named_bar_sync(6, 128);
-                        waited = true;
-                    }
-                    const int q0 = hb * kNA;
-                    const int nq = it.lq - q0 < ncols ? it.lq - q0 : ncols;    // valid query pixels in this half (may be <= 0)
-                    float *dst = og + (long)q0 * qstep;
+            // 16 columns (query pixels) of this thread's channel; `a` = byte address of the first one
+            auto emit16 = [&](const float *o, uint64_t a, int n) {
+                uint64_t a0 = a, a1 = a + qb;
+                const uint64_t qb2 = 2 * qb;
+                if (n >= 16) {
                     if (prod) {
-                        if (p.hints) {
 #pragma unroll
-                            for (int e = 0; e < kMaxCols; ++e)
-                                if (e < nq) st_global_f32(dst + e * qstep, o[e], pol_keep);
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < kMaxCols; ++e)
-                                if (e < nq) st_global_f32(dst + e * qstep, o[e]);
-                        }
-                    } else if (p.hints && one_tile) {              // the one and only add onto these lines: they are final
-#pragma unroll
-                        for (int e = 0; e < kMaxCols; ++e)
-                            if (e < nq) red_global_add_f32(dst + e * qstep, o[e], pol_stream);
+                        for (int e = 0; e < 16; e += 2, a0 += qb2, a1 += qb2) { st_global_f32(a0, o[e], pol); st_global_f32(a1, o[e + 1], pol); }
                     } else {
 #pragma unroll
-                        for (int e = 0; e < kMaxCols; ++e)
-                            if (e < nq) red_global_add_f32(dst + e * qstep, o[e]);
+                        for (int e = 0; e < 16; e += 2, a0 += qb2, a1 += qb2) { red_global_add_f32(a0, o[e], pol); red_global_add_f32(a1, o[e + 1], pol); }
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e, a0 += qb) {
+                        if (e < n) {
+                            if (prod) st_global_f32(a0, o[e], pol);
+                            else red_global_add_f32(a0, o[e], pol);
+                        }
+                    }
+                }
+            };
+            for (int g = 0; g < NG; ++g, ++gc) {
+                float a[16], b[16];
+                mbar_wait(&bars[T_O_FULL + hb], gc & 1);
+                tc_fence_after();
+                tmem_ld16(src, reinterpret_cast<uint32_t *>(a));
+                if (!waited) {                                     // every producer of this sample has stored its tiles (both halves)
+                    if (etid == 0) wait_count(p.cdone + it.b, 2u * (unsigned)p.sp.seg0);
+                    named_bar_sync(6 + hb, 128);
+                    waited = true;
+                }
+                uint64_t dst = o0 + (uint64_t)g * (kGroupCh * 4);
+#pragma unroll 1
+                for (int c0 = 0; c0 < ncols; c0 += 32) {
+                    tmem_ld_wait16(reinterpret_cast<uint32_t *>(a));
+                    if (c0 + 16 < ncols) {
+                        tmem_ld16(src + c0 + 16, reinterpret_cast<uint32_t *>(b));
+                    } else {                                       // the accumulator half is in registers: the MMAs may overwrite it
+                        tc_fence_before();
+                        mbar_arrive(&bars[T_O_EMPTY + hb]);
+                    }
+                    emit16(a, dst, nq - c0);
+                    dst += 16 * qb;
+                    if (c0 + 16 < ncols) {
+                        tmem_ld_wait16(reinterpret_cast<uint32_t *>(b));
+                        if (c0 + 32 < ncols) {
+                            tmem_ld16(src + c0 + 32, reinterpret_cast<uint32_t *>(a));
+                        } else {
+                            tc_fence_before();
+                            mbar_arrive(&bars[T_O_EMPTY + hb]);
+                        }
+                        emit16(b, dst, nq - c0 - 16);
+                        dst += 16 * qb;
                     }
                 }
             }
-            if (prod) {                                            // publish: all stores of this item are visible device-wide
-                __threadfence();
-                named_bar_sync(6, 128);
-                if (tid == 0) {
+            if (prod) {      // publish: the group's stores happen-before the barrier, the fence of its first thread is cumulative
+                named_bar_sync(6 + hb, 128);
+                if (etid == 0) {
                     __threadfence();
                     atomicAdd(p.cdone + it.b, 1u);
                 }
@@ -467,7 +503,7 @@ cudaError_t launch_fwdt(const void *q, const void *k, const void *v, void *out, 
     const int sms = sm_count();
     const int grid = p.sp.total < sms ? p.sp.total : sms;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = FwdTSmem<LK>::kBytes; cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreadsT); cfg.dynamicSmemBytes = FwdTSmem<LK>::kBytes; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;

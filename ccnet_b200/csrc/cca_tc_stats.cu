@@ -195,44 +195,45 @@ cca_tc_stats_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_consta
             // predicated path only for the 16-key chunks that hold the tail of the key block or the self entry of one of this
             // warp's 32 query pixels (warp-uniform test): the masks cost more ALU issue slots than the arithmetic
             const int sw0 = it.col ? it.q0 - it.k0 + 32 * (warp & 3) : -(1 << 20);
-            float m = -INFINITY;                                   // row max of the raw logits (log2e > 0: scale afterwards)
+            // One pass over the S row, 16 columns at a time with the next 16 already in flight from tensor memory: running max m
+            // of the raw logits (log2e > 0: scaled on use) and l = sum 2^((s - m) log2e), rescaled when the max moves; two
+            // accumulators so that the additions do not form one dependent chain.  (Two passes with a wait after every
+            // tcgen05.ld -- max first, then the sum -- made these eight warps the pace of the whole kernel.)
+            float m = -INFINITY, l0 = 0.f, l1 = 0.f;
+            float nx[16];
+            tmem_ld16(ts, reinterpret_cast<uint32_t *>(nx));
 #pragma unroll 1
             for (int c0 = 0; c0 < it.lk; c0 += 16) {
                 float s[16];
-                tmem_ld16(ts + c0, reinterpret_cast<uint32_t *>(s));
-                tmem_ld_wait();
-                const bool masked = (c0 + 16 > it.lk) || (c0 + 16 > sw0 && c0 < sw0 + 32);
-                if (!masked) {
+                tmem_ld_wait16(reinterpret_cast<uint32_t *>(nx));
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) m = fmaxf(m, s[e]);
-                } else {
+                for (int e = 0; e < 16; ++e) s[e] = nx[e];
+                if (c0 + 16 < it.lk) tmem_ld16(ts + c0 + 16, reinterpret_cast<uint32_t *>(nx));
+                const bool masked = (c0 + 16 > it.lk) || (c0 + 16 > sw0 && c0 < sw0 + 32);
+                if (masked) {
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
                         const int j = c0 + e;
-                        m = fmaxf(m, (j < it.lk && j != self) ? s[e] : -INFINITY);
+                        s[e] = (j < it.lk && j != self) ? s[e] : -INFINITY;
                     }
                 }
+                float cm = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
+#pragma unroll
+                for (int e = 4; e < 16; e += 4) cm = fmaxf(cm, fmaxf(fmaxf(s[e], s[e + 1]), fmaxf(s[e + 2], s[e + 3])));
+                if (cm > m) {                                  // (never true for a fully masked chunk: cm = -inf)
+                    const float sc = exp2f((m - cm) * kLog2e);         // m = -inf: exp2(-inf) = 0 and l is still 0
+                    l0 *= sc; l1 *= sc;
+                    m = cm;
+                }
+                const float nm = (m == -INFINITY) ? 0.f : -m * kLog2e;
+#pragma unroll
+                for (int e = 0; e < 16; e += 2) {              // masked entries: exp2(-inf) = 0
+                    l0 += exp2f(fmaf(s[e], kLog2e, nm));
+                    l1 += exp2f(fmaf(s[e + 1], kLog2e, nm));
+                }
             }
+            const float l = l0 + l1;
             m *= kLog2e;
-            const float msub = (m == -INFINITY) ? 0.f : m;
-            float l = 0.f;
-#pragma unroll 1
-            for (int c0 = 0; c0 < it.lk; c0 += 16) {
-                float s[16];
-                tmem_ld16(ts + c0, reinterpret_cast<uint32_t *>(s));
-                tmem_ld_wait();
-                const bool masked = (c0 + 16 > it.lk) || (c0 + 16 > sw0 && c0 < sw0 + 32);
-                if (!masked) {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) l += exp2f(fmaf(s[e], kLog2e, -msub));
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const int j = c0 + e;
-                        l += (j < it.lk && j != self) ? exp2f(fmaf(s[e], kLog2e, -msub)) : 0.f;
-                    }
-                }
-            }
             tc_fence_before();
             mbar_arrive(&bars[SB_S_EMPTY + (k % kNSB)]);
             CCA_STAMP(3);

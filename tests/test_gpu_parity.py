@@ -494,3 +494,45 @@ def test_torch_ops_match_the_functional_path_and_differentiate():
     y.backward(do)
     assert torch.allclose(x.grad, do) and torch.allclose(gamma.grad, (do * ro).sum().reshape(1), rtol=1e-4)
     torch.library.opcheck(torch.ops.cca.forward.default, (q, k, v), test_utils=("test_schema", "test_faketensor"))
+
+
+def test_bf16_long_lines_native_kernels_noise_floor(monkeypatch):
+    """bf16 I/O with lines longer than one tile: the native bf16 kernels (what a direct C-ABI caller gets) add up to 2*ceil(L/112)
+    bf16-rounded partial results per element in no fixed order; their error sits at the 1e-2 budget (one bf16 rounding of the
+    exact gradient alone is 0.3e-2 of max|ref| here), so the Python entry points run such calls on the fp32 kernels and round
+    once (ccnet_b200/functional.py).  This test keeps the native kernels covered, at twice the budget."""
+    from ccnet_b200 import cca_backward, cca_forward
+    O = _oracle()
+    dev = _dev()
+    monkeypatch.setenv("CCA_B200_BF16_NATIVE", "1")
+    shape = (1, 32, 128, 113, 200)
+    q, k, v = _rand_qkv(*shape, seed=41 + sum(shape), scale=0.6, dtype=torch.bfloat16)
+    dout = torch.randn(v.shape, generator=torch.Generator().manual_seed(9)).to(torch.bfloat16)
+    qd, kd, vd, dd = q.to(dev), k.to(dev), v.to(dev), dout.to(dev)
+    out, lse = cca_forward(qd, kd, vd, impl="tc")
+    dq, dk, dv = cca_backward(dd, qd, kd, vd, out, lse, impl="tc")
+    ro, rl = O.cca_forward(q.double(), k.double(), v.double())
+    rq, rk, rv = O.cca_backward(dout.double(), q.double(), k.double(), v.double())
+    assert (out.cpu().double() - ro).abs().max().item() <= 2 * BF16_TOL * max(1.0, ro.abs().max().item())
+    for got, ref, name in ((dq, rq, "dq"), (dk, rk, "dk"), (dv, rv, "dv")):
+        assert got.dtype == torch.bfloat16
+        err = (got.cpu().double() - ref).abs().max().item()
+        assert err <= 2 * BF16_TOL * max(1.0, ref.abs().max().item()), (name, err)
+
+
+def test_forward_channel_major_variant_in_subprocess():
+    """cca_tc_fwdt.cu (opt-in, CCA_B200_FWDT=1: V^T in tensor memory, P^T planes in shared memory, coalesced st / red epilogue):
+    same results as the default values kernel within the fp32 budget, bit-identical across repetitions.  The knob is read once
+    per process, hence the subprocess (tools/r2_probe.py prints one JSON line of errors vs the fp64 oracle)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CCA_B200_FWDT="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "r2_probe.py"), "parity", "2", "64", "512", "97", "97", "fp32"],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    rec = json.loads(r.stdout.strip().splitlines()[-1])
+    assert rec["finite"] and rec["rerun_bit_identical"]
+    assert rec["max_err_rel_to_max_ref"]["out"] <= FP32_TOL and rec["max_abs_err"]["lse"] <= FP32_TOL

@@ -161,13 +161,13 @@ def build(NCH, kNLd, nk):
             if (n & 1) == half:
                 yield from wait_full(slot, g)
                 publish()
-                vb = gcn & 1
-                yield from wait(B["V_EMPTY", vb], ((gcn >> 1) & 1) ^ 1, gcn >> 1)
                 yield
-                rd_cnt[slot] += 4
+                rd_cnt[slot] += 4                            # the slot goes back before the wait for the TMEM buffer
                 if rd_cnt[slot] == 8:
                     rd_cnt[slot] = 0
                     B["LD_EMPTY", slot].arrive(use=g // kNLd)
+                vb = gcn & 1
+                yield from wait(B["V_EMPTY", vb], ((gcn >> 1) & 1) ^ 1, gcn >> 1)
                 yield
                 B["V_FULL", vb].arrive(128, use=gcn >> 1)
             g += 1
