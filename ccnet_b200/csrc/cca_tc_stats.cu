@@ -11,9 +11,11 @@
 //
 // Persistent grid (<= 1 CTA per SM), static round-robin over the items of cca_items.cuh.  Roles:
 //   warp 16 (1 lane)   TMA producer: Q tile, K tile per item, [LK px][64 ch] boxes, ring of 6 slots
-//   warps 8-15         fp32 only: fp32 -> bf16 hi/lo operand planes, in place (convert_slot_inplace)
-//   warp 17            MMA issuer: S = Q K^T (bf16x3 split for fp32 I/O), four S buffers in TMEM
-//   warps 0-3 / 4-7    two statistics groups (TMEM lane == query pixel), alternate items: row max, sum of exp2
+//   warps 8-15         fp32 only: fp32 -> bf16 hi/lo operand planes, in place (256 threads, both 32-channel boxes of a slot)
+//   warp 25            MMA issuer: S = Q K^T (bf16x3 split for fp32 I/O), four S buffers in TMEM
+//   warps 0-7, 16-23   FOUR statistics groups (TMEM lane == query pixel), one S buffer each, items k = g, g+4, ...: the row
+//                      statistics (112 exp2 per thread and item, dependent on tensor-memory loads) are what paces this kernel,
+//                      the conversion of two 28 KB slots per item is not
 //   warps 18-19        clear the per-sample counters of the values kernel (and, if asked, a byte range)
 #include "cca_items.cuh"
 #include "cca_tc_common.cuh"
@@ -23,6 +25,8 @@ namespace {
 using namespace tc;
 
 constexpr int kNS = 6;            // load slots
+constexpr int kStatConvThreads = 256;   // converter threads of this kernel (warps 8-15)
+constexpr int kStatGroups = 4;          // statistics groups: warps 0-3, 4-7, 16-19, 20-23
 constexpr int kNSB = 4;           // S buffers in TMEM (4 x 128 columns)
 
 struct StatsParams {
@@ -75,7 +79,7 @@ cca_tc_stats_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_consta
 
     if (tid == 0) {
         for (int i = 0; i < kNS; ++i) {
-            mbar_init(&bars[SB_LD_FULL + i], 1); mbar_init(&bars[SB_LD_EMPTY + i], 1); mbar_init(&bars[SB_OP_FULL + i], kConvThreads);
+            mbar_init(&bars[SB_LD_FULL + i], 1); mbar_init(&bars[SB_LD_EMPTY + i], 1); mbar_init(&bars[SB_OP_FULL + i], kStatConvThreads);
         }
         for (int i = 0; i < kNSB; ++i) { mbar_init(&bars[SB_S_FULL + i], 1); mbar_init(&bars[SB_S_EMPTY + i], 128); }
         fence_mbar_init();
@@ -151,12 +155,12 @@ cca_tc_stats_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_consta
         for (long i = lo + t; i < hi; i += 64) dst[i] = make_uint4(0, 0, 0, 0);
         if (blockIdx.x == 0)
             for (int i = t; i < p.n_counters; i += 64) p.counters[i] = 0u;
-    } else if (warp >= kWarpConv0) {
+    } else if (warp >= kWarpConv0 && warp < kWarpConv0 + kStatConvThreads / 32) {
         const int t = tid - kWarpConv0 * 32;
         int dbg_n = t == 0 ? 0 : 512;
         (void)dbg_n;
         if constexpr (!BF) {
-            int pend = -1;                       // slot converted but not yet fenced / published (see convert_slot_inplace)
+            int pend = -1;                       // slot converted but not yet fenced / published
             auto publish = [&]() {
                 if (pend >= 0) {
                     fence_proxy_async();
@@ -171,20 +175,50 @@ cca_tc_stats_kernel(const __grid_constant__ CUtensorMap mqc, const __grid_consta
                     mbar_wait(&bars[SB_LD_FULL + slot], (g / kNS) & 1);
                 }
                 CCA_STAMP(1);
-                convert_slot_inplace<LK>(smem + S::off_ld + slot * T::kSlot, t, publish);
+                // both 32-channel boxes of the slot by the same 256 threads (thread = pixel row x 16-channel half): read 2 x 64 B,
+                // meet, overwrite in place as hi/lo planes (layout of convert_slot_inplace)
+                {
+                    using TT = Tiles<LK, false>;
+                    uint8_t *sl = smem + S::off_ld + slot * T::kSlot;
+                    const int r = t & 127, hq = t >> 7;
+                    const int rr = r < LK ? r : LK - 1, sw = rr & 7;
+                    float4 raw[8];
+#pragma unroll
+                    for (int bx = 0; bx < 2; ++bx)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            raw[4 * bx + j] = *reinterpret_cast<const float4 *>(sl + bx * TT::kTile + rr * 128 + (((hq * 4 + j) ^ sw) * 16));
+                    publish();
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (r < LK) {
+#pragma unroll
+                        for (int bx = 0; bx < 2; ++bx) {
+                            uint8_t *d = sl + bx * TT::kTile + r * 16 + hq * 2 * TT::kPStride;
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const float4 a = raw[4 * bx + 2 * j], b = raw[4 * bx + 2 * j + 1];
+                                const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                                uint4 hi, lo;
+                                split8(v, hi, lo);
+                                *reinterpret_cast<uint4 *>(d + j * TT::kPStride) = hi;
+                                *reinterpret_cast<uint4 *>(d + j * TT::kPStride + TT::kLoOff) = lo;
+                            }
+                        }
+                    }
+                }
                 pend = slot;
                 CCA_STAMP(1);
             }
             publish();
         }
         (void)t;
-    } else {
-        // =============================== statistics groups (2 x 128 threads, TMEM lane == query pixel) ===============================
-        const int grp = warp >> 2, r = tid & 127;
+    } else if (warp < 8 || (warp >= 16 && warp < 24)) {
+        // =============================== statistics groups (4 x 128 threads, TMEM lane == query pixel) ===============================
+        const int grp = warp < 8 ? warp >> 2 : 2 + ((warp - 16) >> 2), r = tid & 127;
         const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         int dbg_n = tid == 0 ? 0 : 512;          // group 0 only (role 3)
         (void)dbg_n;
-        for (int k = grp; k < nk; k += 2) {
+        for (int k = grp; k < nk; k += kStatGroups) {
             const Item it = item_of(k);
             CCA_STAMP(3);
             mbar_wait(&bars[SB_S_FULL + (k % kNSB)], (k / kNSB) & 1);
