@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.environ.get("CCA_B200_LIBDIR") or os.path.join(HERE, "lib")      # (override: a second, profiling flavour)
 LIB = os.path.join(LIBDIR, "libcca_b200.so")
-SOURCES = ["cca_capi.cu", "cca_simt.cu", "cca_tc_host.cu", "cca_tc_stats.cu", "cca_tc_fwd.cu", "cca_tc_fwdt.cu", "cca_tc_bwd.cu", "cca_gemm.cu"]
+SOURCES = ["cca_capi.cu", "cca_simt.cu", "cca_tc_host.cu", "cca_tc_stats.cu", "cca_tc_fwd.cu", "cca_tc_bwd.cu", "cca_gemm.cu"]
 HEADERS = ["cca_common.cuh", "cca_sm100.cuh", "cca_tc_common.cuh", "cca_items.cuh", "../../include/cca_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

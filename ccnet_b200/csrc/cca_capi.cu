@@ -46,7 +46,7 @@ int env_int(const char *name, int dflt, int lo, int hi)
     return v < lo || v > hi ? dflt : v;
 }
 constexpr int kUnset = -1000;
-std::atomic<int> g_pdl{kUnset}, g_zero_ahead{kUnset}, g_delta{kUnset}, g_lag{kUnset}, g_hints{kUnset}, g_fwdt{kUnset};
+std::atomic<int> g_pdl{kUnset}, g_zero_ahead{kUnset}, g_delta{kUnset}, g_lag{kUnset}, g_hints{kUnset};
 int knob(std::atomic<int> &g, const char *name, int dflt, int lo, int hi)
 {
     int v = g.load(std::memory_order_relaxed);
@@ -62,14 +62,12 @@ int tc_zero_ahead() { return knob(g_zero_ahead, "CCA_B200_ZERO_AHEAD", 1, 1, 4);
 int tc_delta_mode() { return knob(g_delta, "CCA_B200_DELTA", -1, -1, 1); }
 int tc_lag() { return knob(g_lag, "CCA_B200_LAG", -1, -1, 1); }
 int tc_l2_hints() { return knob(g_hints, "CCA_B200_L2HINT", 1, 0, 2); }
-int tc_fwdt() { return knob(g_fwdt, "CCA_B200_FWDT", 0, 0, 1); }
 #ifdef CCA_DEBUG_HOOKS
 void set_tc_pdl(int on) { g_pdl.store(on ? 1 : 0); }
 void set_tc_zero_ahead(int n) { g_zero_ahead.store(n < 1 ? 1 : (n > 4 ? 4 : n)); }
 void set_tc_delta_mode(int m) { g_delta.store(m < -1 || m > 1 ? -1 : m); }
 void set_tc_lag(int v) { g_lag.store(v < -1 || v > 1 ? -1 : v); }
 void set_tc_l2_hints(int v) { g_hints.store(v < 0 || v > 2 ? 1 : v); }
-void set_tc_fwdt(int v) { g_fwdt.store(v ? 1 : 0); }
 #endif
 }  // namespace cca
 
@@ -88,7 +86,6 @@ CCA_API void cca_b200__set_zero_ahead(int n) { set_tc_zero_ahead(n); }
 CCA_API void cca_b200__set_delta_mode(int m) { set_tc_delta_mode(m); }
 CCA_API void cca_b200__set_lag(int v) { set_tc_lag(v); }
 CCA_API void cca_b200__set_l2_hints(int v) { set_tc_l2_hints(v); }
-CCA_API void cca_b200__set_fwdt(int v) { set_tc_fwdt(v); }
 #endif
 const char *cca_b200_last_error(void) { return g_err; }
 const char *cca_b200_strerror(int s)

@@ -43,10 +43,6 @@ bool tc_forward_supported(Dims d, int dtype);
 size_t tc_forward_workspace(Dims d);
 cudaError_t tc_forward(const void *q, const void *k, const void *v, void *out, float *lse, void *ws,
                        Dims d, int dtype, cudaStream_t st, const char **why);
-// channel-major values kernel (cca_tc_fwdt.cu: fp32, C % 128 == 0); the statistics pre-pass is launched by tc_forward
-bool tc_forward_t_supported(Dims d, int dtype);
-cudaError_t tc_forward_values_t(const void *q, const void *k, const void *v, void *out, float *lse, const float *parts,
-                                unsigned int *cdone, Dims d, int lk, cudaStream_t st, const char **why);
 // statistics pre-pass of the tensor-core forward (cca_tc_stats.cu): partial lse planes; also clears a byte range and counters
 cudaError_t tc_stats(const void *q, const void *k, float *parts, void *zero_ptr, long zero_bytes, unsigned int *counters,
                      int n_counters, Dims d, int dtype, cudaStream_t st, const char **why);
@@ -75,20 +71,17 @@ void count_launch(int n = 1);
 //   CCA_B200_DELTA = -1/0/1   backward: -1 automatic, 0 every item computes delta, 1 column items produce it for the sample
 //   CCA_B200_LAG = 0/1        item order: consumers of a sample trail its producers by one block (default 1)
 //   CCA_B200_L2HINT = 0/1     L2 eviction hints on the bulk copies (default 1)
-//   CCA_B200_FWDT = 0/1       fp32 forward: channel-major values kernel (cca_tc_fwdt.cu; default 0 until validated on the GPU) or cca_tc_fwd.cu
 int tc_pdl();
 int tc_zero_ahead();
 int tc_delta_mode();
 int tc_lag();          // -1 = per-kernel default
 int tc_l2_hints();
-int tc_fwdt();
 #ifdef CCA_DEBUG_HOOKS
 void set_tc_pdl(int on);
 void set_tc_zero_ahead(int n);
 void set_tc_delta_mode(int m);
 void set_tc_lag(int v);
 void set_tc_l2_hints(int v);
-void set_tc_fwdt(int v);
 void set_tc_debug_buffer(void *p);
 void set_tc_bwd_debug_buffer(void *p);
 void set_tc_stats_debug_buffer(void *p);

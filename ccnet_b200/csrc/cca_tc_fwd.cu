@@ -531,8 +531,6 @@ cudaError_t tc_forward(const void *q, const void *k, const void *v, void *out, f
     cudaError_t e = tc_stats(q, k, parts, nullptr, 0, cdone, d.B, d, dtype, st, why);
     if (e != cudaSuccess) return e;
     const int lk = lk_for(max_tile(sp));
-    if (tc_fwdt() && lk == 112 && tc_forward_t_supported(d, dtype))   // opt-in experiment (cca_tc_fwdt.cu): fp32, C % 128 == 0, 112-pixel tiles
-        return tc_forward_values_t(q, k, v, out, lse, parts, cdone, d, lk, st, why);
     if (bf)
         return lk == 80 ? launch_fwd<80, true>(q, k, v, out, lse, parts, cdone, d, st, why)
                         : launch_fwd<112, true>(q, k, v, out, lse, parts, cdone, d, st, why);

@@ -1,4 +1,4 @@
-"""Discrete model of the mbarrier protocol of cca_tc_fwdt.cu (roles as coroutines, random interleavings).
+"""Discrete model of the mbarrier protocol of tools/experiments/cca_tc_fwdt.cu (roles as coroutines, random interleavings).
 
 Not a performance model: it only answers "can this hand-shake deadlock, and does every arrive / wait hit the barrier
 phase it was meant for?" before GPU minutes are spent on it.  Every wait and arrive carries the use index the code
