@@ -84,9 +84,10 @@ def bind_to_gpu_numa_node(local_rank: int):
 
 def ncu_traffic(dtype_name: str):
     """DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of one op forward / backward, parsed from the committed
-    ncu summary of tools/run_op.py (BASELINE config 2, fp32).  Returns None when no capture matches."""
-    path = os.path.join(ROOT, "profiles", "r02_tc_ncu_summary.txt")
-    if dtype_name != "f32" or not os.path.exists(path):
+    ncu summary of tools/run_op.py (BASELINE config 2, fp32 or bf16).  Returns None when no capture matches."""
+    fname = "r02_tc_ncu_summary.txt" if dtype_name == "f32" else "r02_tc_ncu_summary_bf16.txt"
+    path = os.path.join(ROOT, "profiles", fname)
+    if not os.path.exists(path):
         return None
     units = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}
     tot = {"fwd": 0.0, "bwd": 0.0}
@@ -100,7 +101,7 @@ def ncu_traffic(dtype_name: str):
             tot[cur] += float(f[1].replace(",", "")) * units.get(f[2].lower(), 1.0)
     if tot["fwd"] == 0.0 or tot["bwd"] == 0.0:
         return None
-    return {"fwd": tot["fwd"], "bwd": tot["bwd"], "source": "profiles/r02_tc_ncu_summary.txt"}
+    return {"fwd": tot["fwd"], "bwd": tot["bwd"], "source": "profiles/" + fname}
 
 
 def measured_peaks():
