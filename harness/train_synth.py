@@ -91,7 +91,7 @@ def run(local_rank: int, world: int, steps: int = 5, warmup: int = 2, crop: int 
     # sees [per_gpu, 512, crop/8 + 1, crop/8 + 1]
     hw = (crop - 1) // 8 + 1
     rc = RCCA(512, recurrence=recurrence).to(dev)
-    rc.cca.load_state_dict(net.module.head.cca.state_dict() if world > 1 else net.head.cca.state_dict())
+    rc.cca.load_state_dict(net.head.cca.state_dict())      # `net` is the bare network, `model` its DDP wrapper
     xh = torch.randn(per_gpu, 512, hw, hw, device=dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
     gh = torch.randn_like(xh)
 
@@ -106,7 +106,7 @@ def run(local_rank: int, world: int, steps: int = 5, warmup: int = 2, crop: int 
     out["cca_share_of_train_step"] = ms_cca / ms_train
     out["head_feature_map"] = [per_gpu, 512, hw, hw]
     if forward_only_too and local_rank == 0:
-        net_eval = (net.module if world > 1 else net)
+        net_eval = net
         x1 = images[:1]
 
         def fwd():
