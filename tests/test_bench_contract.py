@@ -8,7 +8,7 @@ import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-ALL = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01e_bench_line*.json")))
+ALL = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01e_bench_line*.json")) + glob.glob(os.path.join(ROOT, "profiles", "r02_bench_line*.json")))
 LINES = [p for p in ALL if "reference_arm" not in p]
 REF_LINES = [p for p in ALL if "reference_arm" in p]
 
@@ -29,6 +29,12 @@ def test_committed_bench_line_has_the_contract_fields(path):
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert r["traffic"] is None or r["traffic"] > 0
+    if os.path.basename(path).startswith("r02"):            # round 2: traffic parsed from the committed ncu summary, both ops reported
+        assert r["traffic"] and r["traffic_source"].startswith("profiles/r02_tc_ncu_summary")
+        assert r["op_fwd"]["frac"] > 0.38 and r["op_bwd"]["frac"] > 0.34 and r["other_dtype"]["dtype"] == "bf16"
+        assert "module" in d and d["module"]["ms_per_step"] < 4.0
+        if "error" not in (d.get("ccnet") or {"error": 1}):
+            assert d["ccnet"]["train_images_per_s"] > 0 and d["ccnet"]["per_gpu_batch"] * d["n_gpus"] == 8
     e = d["e2e"]
     assert e["h2d_bytes_per_step"] == 8 * 512 * 97 * 97 * 4 and e["d2h_bytes_per_step"] == 2 * e["h2d_bytes_per_step"]
     assert e["value"] < d["value"]                          # host copies + the module's projections are inside e2e
@@ -44,7 +50,8 @@ def test_committed_bench_line_has_the_contract_fields(path):
 def test_committed_reference_arm_line(path):
     """`bench.py --impl reference`: same metric / unit / config as our arm, the CPU reference timed on the host cores."""
     d = json.load(open(path))
-    ours = json.load(open(LINES[0]))
+    same_round = [p for p in LINES if os.path.basename(p)[:3] == os.path.basename(path)[:3]]
+    ours = json.load(open((same_round or LINES)[0]))
     assert d["impl"] == "reference" and d["metric"] == ours["metric"] and d["unit"] == ours["unit"]
     assert d["higher_is_better"] is True and d["config"]["workload"] == ours["config"]["workload"]
     b = d["cpu_baseline"]
