@@ -45,7 +45,10 @@ extern "C" {
 
 typedef enum cca_dtype {
     CCA_F32 = 0,  /* float32 I/O, fp32 accumulate                                       */
-    CCA_BF16 = 1  /* bfloat16 I/O, fp32 accumulate, fp32 lse                            */
+    CCA_BF16 = 1  /* bfloat16 I/O, fp32 accumulate, fp32 lse.  Lines longer than 112 pixels: an */
+                  /* output element is the sum of up to 2*ceil(L/112) bf16-rounded partial      */
+                  /* results (TMA reduce-add, no fixed order): gradients at the 1e-2 budget --  */
+                  /* call CCA_F32 on upcast tensors for fp32-grade accumulation */
 } cca_dtype;
 
 typedef enum cca_status {
