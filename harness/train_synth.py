@@ -54,7 +54,12 @@ def run(local_rank: int, world: int, steps: int = 5, warmup: int = 2, crop: int 
     with torch.no_grad():
         net.head.cca.gamma.fill_(0.5)                             # gamma = 0 at init would make the operator's output vanish
     if world > 1:
-        net = nn.SyncBatchNorm.convert_sync_batchnorm(net)
+        # (torch.nn.SyncBatchNorm copies a mask to the host in every layer's forward: harness/sync_bn.py; HARNESS_SYNCBN=torch selects it)
+        if os.environ.get("HARNESS_SYNCBN", "") == "torch":
+            net = nn.SyncBatchNorm.convert_sync_batchnorm(net)
+        else:
+            from harness.sync_bn import convert_sync_batchnorm
+            net = convert_sync_batchnorm(net)
         model = nn.parallel.DistributedDataParallel(net, device_ids=[local_rank])
     else:
         model = net
